@@ -1,0 +1,100 @@
+"""ctypes binding of libevfly_b200.so (the C ABI declared in include/evfly_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing, importing a product path
+raises. Nothing in this package computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libevfly_b200.so")
+HEADER_PATH = os.path.join(PKG_DIR, "..", "include", "evfly_b200.h")
+
+# ---- constants mirrored from the header ---------------------------------------------------
+POL_NEG, POL_POS, POL_SKIP = 0, 1, 2
+NEG_IS_ZERO, NEG_IS_NEGATIVE = 0, 1
+U8_WRAP, U8_SATURATE = 0, 1
+
+
+class EvflyError(RuntimeError):
+    pass
+
+
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+
+# name -> (restype, argtypes); every symbol include/evfly_b200.h declares must be listed here
+# (tests/test_abi.py cross-checks this table against the header).
+SIGNATURES = {
+    "evfly_abi_version": (_i32, []),
+    "evfly_last_error": (C.c_char_p, []),
+    "evfly_launch_count": (_i64, []),
+    "evfly_pack_events_f64": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _f64, _f64, _i64, _vp, _vp, _vp, _vp]),
+    "evfly_pack_events_soa": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "evfly_accumulate_counts": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "evfly_counts_to_frame_f64": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _vp]),
+    "evfly_counts_to_u8": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "evfly_u8_saturate_replay": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "evfly_voxel_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "evfly_voxelize_window": (_i32, [_vp, _i64, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "evfly_accumulate_windows": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "evfly_decode_crop": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
+    "evfly_quantile_scale_clip": (_i32, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def header_symbols() -> list[str]:
+    """Function names declared in include/evfly_b200.h."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(evfly_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed for loading) and set the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EvflyError(
+            f"{LIB_PATH} is missing. Build it with `python -m evfly_b200._build` "
+            "(__graft_entry__.build()). evfly_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.evfly_abi_version() != 1:
+        raise EvflyError("libevfly_b200.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().evfly_last_error().decode(errors="replace")
+        raise EvflyError(f"{what or 'libevfly_b200'} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """data_ptr of a CUDA tensor (None -> NULL). Refuses host tensors: the ABI is device-only."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EvflyError("libevfly_b200 takes device pointers only; got a CPU tensor")
+    if not t.is_contiguous():
+        raise EvflyError("libevfly_b200 takes contiguous tensors only")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().evfly_launch_count())

@@ -1,0 +1,190 @@
+/*
+ * evfly_b200.h -- C ABI of libevfly_b200.so: the B200 (sm_100a) implementation of
+ * evfly's perception hot path (event accumulation -> frame normalisation ->
+ * depth-pretext UNet/ConvLSTM -> ViT-LSTM velocity forward).
+ *
+ * Conventions:
+ *   - every pointer named d_* is CALLER-OWNED DEVICE memory (e.g. a torch tensor's
+ *     data_ptr()); the library keeps no reference after the call is enqueued;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no
+ *     hidden device synchronisation and no allocation, and is safe to capture in a CUDA graph;
+ *   - scratch memory is caller-owned too: ask evfly_*_workspace_bytes() and pass a buffer;
+ *     scratch that must be zero on entry is documented as such and is LEFT ZERO on exit;
+ *   - return value 0 on success, a negative EVFLY_ERR_* otherwise; evfly_last_error()
+ *     returns a thread-local human-readable message. No exception crosses the ABI;
+ *   - there is no CPU fallback anywhere in the library.
+ *
+ * Reference interfaces replaced (paths relative to the evfly tree):
+ *   evfly_ros/src/node.cpp:24-59        ImagePublisher::eventArrayCallback/timerCallback (u8, wraps)
+ *   evfly_dv_ros/src/node.cpp:24-63     same for DAVIS (u8, saturates at 0/255)
+ *   utils/ev_utils.py:113-161           form_eventframe (np.histogram2d signed count frame)
+ *   utils/to_events.py:400-411          per-window slicing of one continuous stream
+ *   evfly_ros/run.py:334-350,250-253    u8 decode, centre-crop, 97th-percentile scale + clip
+ *   learner/dataloading.py:518-521,531-533  per-frame percentile scale, clamp, min-cutoff
+ *   learner/learner_models.py, learner/vitfly_models.py, learner/ViTsubmodules.py,
+ *   learner/ConvLSTM_pytorch/convlstm.py    model forward (see the model section below)
+ */
+#ifndef EVFLY_B200_H
+#define EVFLY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVFLY_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------- */
+#define EVFLY_OK                 0
+#define EVFLY_ERR_INVALID_ARG   -1   /* null pointer, negative size, unsupported shape ...   */
+#define EVFLY_ERR_CUDA          -2   /* a CUDA runtime call failed (message has the detail) */
+#define EVFLY_ERR_WORKSPACE     -3   /* workspace too small                                 */
+#define EVFLY_ERR_UNSUPPORTED   -4   /* configuration not implemented                       */
+
+/* ---- the packed event record ---------------------------------------------------------
+ * 16 bytes, identical to the in-memory layout of dv_ros_msgs::Event /
+ * prophesee_event_msgs::Event (dv_ros_msgs/msg/Event.msg:2-5: uint16 x, uint16 y, time ts,
+ * bool polarity; ros::Time is {uint32 sec, uint32 nsec}), so a ROS node can memcpy
+ * msg->events.data() straight into a pinned staging buffer. One ld.global.v4.b32 per event.
+ * polarity: 1 = positive (++), 0 = negative (--), >= 2 = record is skipped (written by the
+ * packers for events that the reference's masks drop; never produced by a sensor).        */
+typedef struct evfly_event {
+    uint16_t x;
+    uint16_t y;
+    uint32_t ts_sec;
+    uint32_t ts_nsec;
+    uint8_t  polarity;
+    uint8_t  pad[3];
+} evfly_event;
+
+#define EVFLY_POL_NEG   0
+#define EVFLY_POL_POS   1
+#define EVFLY_POL_SKIP  2
+
+/* polarity convention of the float [t,x,y,p] rows handed to form_eventframe            */
+#define EVFLY_NEG_IS_ZERO      0   /* all_events=True : pos p>0, neg p==0 (ev_utils.py:155-156) */
+#define EVFLY_NEG_IS_NEGATIVE  1   /* timed / to_events: pos p>0, neg p<0 (ev_utils.py:137-138) */
+
+/* u8 accumulator overflow behaviour */
+#define EVFLY_U8_WRAP      0   /* evfly_ros/src/node.cpp:33-37 (uint8 ++/-- wraps mod 256)   */
+#define EVFLY_U8_SATURATE  1   /* evfly_dv_ros/src/node.cpp:33-41 (clamps at 0 / 255)        */
+
+/* ---- library ------------------------------------------------------------------------ */
+int         evfly_abi_version(void);
+const char* evfly_last_error(void);
+/* number of kernel launches this process has enqueued through the library (bench.py's
+ * gpu_launches claim is read from here).                                                 */
+int64_t     evfly_launch_count(void);
+
+/* ======================================================================================
+ * L1  event accumulation
+ * ====================================================================================== */
+
+/* Pack float64 rows [n,4] = (t, x, y, p) -- the argument form_eventframe receives -- into
+ * evfly_event records, applying exactly the reference's masks:
+ *   - np.histogram2d binning over range [0,W]x[0,H] with W x H unit bins: bin = floor(coord),
+ *     the right edge is included (x == W -> bin W-1), everything else (incl. NaN) dropped;
+ *   - polarity classes per `pol_mode`;
+ *   - if use_time: keep only t_lo <= t < t_hi, compared in float64 like ev_utils.py:128
+ *     (the caller passes times0*1e9 and times1[0]*1e9 computed in float64);
+ *   - if max_events >= 0 (the `N is not None` branch, ev_utils.py:130-133): keep only the first
+ *     max_events rows with t >= t_lo; *d_last_kept_t receives the t of the last kept row.
+ * Dropped rows become polarity=EVFLY_POL_SKIP records, so out[i] always corresponds to row i.
+ * ts is floor(t) split into sec/nsec (t is in ns, ev_utils.py:128).
+ * d_scan_ws: (n/1024+2)*8 bytes of scratch, only needed when max_events >= 0.            */
+int evfly_pack_events_f64(const double* d_rows, int64_t n, int H, int W, int pol_mode,
+                          int use_time, double t_lo, double t_hi, int64_t max_events,
+                          evfly_event* d_out, double* d_last_kept_t, void* d_scan_ws,
+                          void* stream);
+
+/* Pack structure-of-arrays streams (utils/to_events.py:400-411: events[traj]['x','y','t','p']
+ * with p in {+1,-1} and t in ns) into records. Any of the integer types is given as int64. */
+int evfly_pack_events_soa(const int64_t* d_x, const int64_t* d_y, const int64_t* d_t_ns,
+                          const int64_t* d_p, int64_t n, int H, int W, int pol_mode,
+                          evfly_event* d_out, void* stream);
+
+/* counts[pol][y][x] += #events, pol 0 = negative plane, 1 = positive plane; int32 [2,H,W].
+ * Events with x >= W or y >= H (unsigned compare, node.cpp:31) or polarity >= 2 are ignored.
+ * The caller zeroes d_counts (or keeps accumulating into it across calls, which is how the
+ * ROS callbacks between two timer ticks are served).                                      */
+int evfly_accumulate_counts(const evfly_event* d_events, int64_t n, int H, int W,
+                            int32_t* d_counts, void* stream);
+
+/* float64 frame[y][x] = pos_thresh*counts[1] - neg_thresh*counts[0], evaluated with exactly
+ * that expression in IEEE double (no FMA contraction) so it is bit-identical to
+ * ev_utils.py:158/:141 on the same counts.                                                */
+int evfly_counts_to_frame_f64(const int32_t* d_counts, int H, int W, double pos_thresh,
+                              double neg_thresh, double* d_frame, void* stream);
+
+/* u8 publish step of the two C++ nodes (timerCallback): frame_out = apply(state_in, counts).
+ * WRAP    : (state + npos - nneg) mod 256                      -- exact for any event order.
+ * SATURATE: state + npos - nneg when state+npos <= 255 and state-nneg >= 0 (then no clamp can
+ *           have fired whatever the order); other pixels are order dependent: they are
+ *           written with the clamped order-free value, their linear index is appended to
+ *           d_flagged (capacity flagged_cap) and *d_n_flagged counts them. The caller then
+ *           runs evfly_u8_saturate_replay() over the window's events to make them exact.
+ * d_state_in may be NULL (= all 128, the value timerCallback resets to). d_n_flagged must be
+ * zero on entry in SATURATE mode.                                                         */
+int evfly_counts_to_u8(const int32_t* d_counts, int H, int W, int mode,
+                       const uint8_t* d_state_in, uint8_t* d_frame_out,
+                       int32_t* d_flagged, int32_t flagged_cap, int32_t* d_n_flagged,
+                       void* stream);
+
+/* Exact in-order replay (evfly_dv_ros/src/node.cpp:33-41) of the pixels listed in d_flagged:
+ * one CTA per flagged pixel folds the clamp-add steps of all n events in stream order.
+ * n_flagged is a host value (the caller reads *d_n_flagged when it fetches the frame).     */
+int evfly_u8_saturate_replay(const evfly_event* d_events, int64_t n, int H, int W,
+                             const uint8_t* d_state_in, const int32_t* d_flagged,
+                             int32_t n_flagged, uint8_t* d_frame_out, void* stream);
+
+/* One window [t0_ns, t1_ns) of one stream -> int32 counts [2,H,W] (may be NULL) and a fp32
+ * voxel grid [B,H,W] with bilinear weights in time (build-defined, SURVEY.md F1: the
+ * reference has no voxel grid):
+ *     tau_i = (B-1) * (t_i - t0) / (t1 - t0),   V[b,y,x] = sum_i pol_i * max(0, 1 - |b - tau_i|)
+ * Events outside the window are ignored. d_counts / d_voxel must be zero on entry.
+ * `algo`: 0 = direct (RED.s32 + 2x RED.f32 into the outputs),
+ *         1 = staged (one red.global.add.v4.f32 per event into d_ws, then a finalise kernel).
+ * d_ws: evfly_voxel_workspace_bytes(H,W,B) bytes, zero on entry, left zero on exit (algo 1). */
+int64_t evfly_voxel_workspace_bytes(int H, int W, int B);
+int evfly_voxelize_window(const evfly_event* d_events, int64_t n, int H, int W, int B,
+                          int64_t t0_ns, int64_t t1_ns, int32_t* d_counts, float* d_voxel,
+                          void* d_ws, int algo, void* stream);
+
+/* T windows of one stream in one pass (utils/to_events.py:400-411 rescans the stream T times):
+ * window w = [edges[w], edges[w+1]) with d_edges_ns int64[T+1] ascending.
+ * d_counts int32 [T,2,H,W], d_voxel fp32 [T,B,H,W] or NULL (B ignored then).
+ * Outputs need NOT be zero on entry: the call zero-fills them itself, a group of windows at
+ * a time, so that a group's lines are still in L2 when its events are scattered.
+ * sorted_by_time != 0 promises ascending t (ROS streams are); then each group only reads its
+ * own slice of the stream. With 0 every group pass reads the whole stream (still exact).   */
+int evfly_accumulate_windows(const evfly_event* d_events, int64_t n, const int64_t* d_edges_ns,
+                             int T, int H, int W, int B, int32_t* d_counts, float* d_voxel,
+                             int sorted_by_time, int64_t* d_range_ws /* int64[T+1] */,
+                             void* stream);
+
+/* ======================================================================================
+ * L2  frame normalisation
+ * ====================================================================================== */
+
+/* evfly_ros/run.py:334-336,345-350: (u8 -> f32 - 128) * 0.2, centre crop
+ * rows H/2-h/2 : H/2+h/2, cols W/2-w/2 : W/2+w/2. N frames. Also accepts int32 counts
+ * [N,2,H,W] (d_u8 NULL): frame = 0.2f * (npos - nneg) in fp32, which equals the fp32 cast of
+ * the reference's fp64 frame for |npos-nneg| < 2^22.                                        */
+int evfly_decode_crop(const uint8_t* d_u8, const int32_t* d_counts, int N, int H, int W,
+                      int h, int w, float scale, float* d_out, void* stream);
+
+/* Per-frame q = quantile(|x|, qfrac) with torch.quantile's linear interpolation, computed
+ * EXACTLY by radix-select on the fp32 bit patterns (no sort), then
+ * out = clip(x / q, lo, hi) (run.py:250-253; dataloading.py:518-521) and, if cutoff > 0,
+ * |out| < cutoff -> 0 (dataloading.py:531-533 / learner_models.py:477).
+ * d_q (may be NULL) receives the N quantiles. One CTA per frame; the frame is re-read from L2.
+ * In-place (d_out == d_x) is allowed.                                                      */
+int evfly_quantile_scale_clip(const float* d_x, int N, int64_t elems_per_frame, float qfrac,
+                              float lo, float hi, float cutoff, float* d_out, float* d_q,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVFLY_B200_H */
