@@ -1,0 +1,111 @@
+"""Drop-in for evfly's learner/ViTsubmodules.py (same class names, constructor signatures,
+parameter names and forward signatures), computed by libevfly_b200 kernels.
+
+Token tensors are [B, N, C] contiguous; every flatten/transpose/permute of the reference
+(ViTsubmodules.py:31-32,65-72,108-114,147) is a strided VIEW handed to the conv kernel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._modbase import PackedModule
+
+
+def _bchw_view(tok: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """[B, H*W, C] tokens seen as [B, C, H, W] (no copy)."""
+    B, N, C = tok.shape
+    return tok.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+class OverlapPatchMerging(PackedModule):
+    def __init__(self, in_channels, out_channels, patch_size, stride, padding):
+        super().__init__()
+        self.cn1 = nn.Conv2d(in_channels, out_channels, kernel_size=patch_size, stride=stride, padding=padding)
+        self.layerNorm = nn.LayerNorm(out_channels)
+
+    def forward(self, patches):
+        """(B,C,H,W) -> tokens (B, H'*W', C_out), H', W'   (ViTsubmodules.py:21-34)"""
+        B, _, H, W = patches.shape
+        c = self.cn1
+        k, s, p = c.kernel_size[0], c.stride[0], c.padding[0]
+        OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        tok = torch.empty((B, OH * OW, c.out_channels), dtype=torch.float32, device=patches.device)
+        ops.conv2d(patches, c.weight, c.bias, stride=s, pad=p, out_view=_bchw_view(tok, OH, OW))
+        ln = self.layerNorm
+        return ops.layernorm(tok, ln.weight, ln.bias, ln.eps), OH, OW
+
+
+class EfficientSelfAttention(PackedModule):
+    def __init__(self, channels, reduction_ratio, num_heads):
+        super().__init__()
+        assert channels % num_heads == 0, f"channels {channels} should be divided by num_heads {num_heads}."
+        self.heads = num_heads
+        self.cn1 = nn.Conv2d(in_channels=channels, out_channels=channels, kernel_size=reduction_ratio, stride=reduction_ratio)
+        self.ln1 = nn.LayerNorm(channels)
+        self.keyValueExtractor = nn.Linear(channels, channels * 2)
+        self.query = nn.Linear(channels, channels)
+        self.smax = nn.Softmax(dim=-1)
+        self.finalLayer = nn.Linear(channels, channels)
+
+    def forward(self, x, H, W, residual=None):
+        """(B,N,C) -> (B,N,C); with `residual` the sum residual + attn(x) is returned (the
+        caller's `x = x + attn(x)`, ViTsubmodules.py:144, fused into the last GEMM's epilogue)."""
+        B, N, C = x.shape
+        r = self.cn1.stride[0]
+        h2, w2 = (H - r) // r + 1, (W - r) // r + 1
+        red = torch.empty((B, h2 * w2, C), dtype=torch.float32, device=x.device)
+        ops.conv2d(_bchw_view(x, H, W), self.cn1.weight, self.cn1.bias, stride=r, out_view=_bchw_view(red, h2, w2))
+        red = ops.layernorm(red, self.ln1.weight, self.ln1.bias, self.ln1.eps)
+        kv = ops.linear(red.view(-1, C), self.keyValueExtractor.weight, self.keyValueExtractor.bias).view(B, h2 * w2, 2 * C)
+        q = ops.linear(x.view(-1, C), self.query.weight, self.query.bias).view(B, N, C)
+        att = ops.attention_small(q, kv, self.heads)
+        out = ops.linear(att.view(-1, C), self.finalLayer.weight, self.finalLayer.bias,
+                         res2d=None if residual is None else residual.view(-1, C))
+        return out.view(B, N, C)
+
+
+class MixFFN(PackedModule):
+    def __init__(self, channels, expansion_factor):
+        super().__init__()
+        expanded_channels = channels * expansion_factor
+        self.mlp1 = nn.Linear(channels, expanded_channels)
+        self.depthwise = nn.Conv2d(expanded_channels, expanded_channels, kernel_size=3, padding='same', groups=channels)
+        self.gelu = nn.GELU()
+        self.mlp2 = nn.Linear(expanded_channels, channels)
+
+    def forward(self, x, H, W, residual=None):
+        """(B,N,C) -> (B,N,C): Linear, grouped 3x3 conv ('same'), exact GELU, Linear
+        (ViTsubmodules.py:105-120). GELU rides in the conv epilogue, the residual in mlp2's."""
+        B, N, C = x.shape
+        Ce = self.mlp1.out_features
+        y1 = ops.linear(x.view(-1, C), self.mlp1.weight, self.mlp1.bias).view(B, N, Ce)
+        y2 = torch.empty_like(y1)
+        ops.conv2d(_bchw_view(y1, H, W), self.depthwise.weight, self.depthwise.bias, pad=1, groups=self.depthwise.groups,
+                   act="gelu", out_view=_bchw_view(y2, H, W))
+        out = ops.linear(y2.view(-1, Ce), self.mlp2.weight, self.mlp2.bias,
+                         res2d=None if residual is None else residual.view(-1, C))
+        return out.view(B, N, C)
+
+
+class MixTransformerEncoderLayer(PackedModule):
+    def __init__(self, in_channels, out_channels, patch_size, stride, padding,
+                 n_layers, reduction_ratio, num_heads, expansion_factor):
+        super().__init__()
+        self.patchMerge = OverlapPatchMerging(in_channels, out_channels, patch_size, stride, padding)
+        self._attn = nn.ModuleList([EfficientSelfAttention(out_channels, reduction_ratio, num_heads) for _ in range(n_layers)])
+        self._ffn = nn.ModuleList([MixFFN(out_channels, expansion_factor) for _ in range(n_layers)])
+        self._lNorm = nn.ModuleList([nn.LayerNorm(out_channels) for _ in range(n_layers)])
+
+    def forward(self, x):
+        """(B,C,H,W) -> (B,C',H',W') (a channel-last view; ViTsubmodules.py:132-148)."""
+        self._check_inference()
+        B = x.shape[0]
+        tok, H, W = self.patchMerge(x)
+        for i in range(len(self._attn)):
+            tok = self._attn[i].forward(tok, H, W, residual=tok)
+            tok = self._ffn[i].forward(tok, H, W, residual=tok)
+            ln = self._lNorm[i]
+            tok = ops.layernorm(tok, ln.weight, ln.bias, ln.eps)
+        return _bchw_view(tok, H, W)

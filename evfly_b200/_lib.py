@@ -44,6 +44,35 @@ SIGNATURES = {
     "evfly_quantile_scale_clip": (_i32, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
 }
 
+
+
+class ConvArgs(C.Structure):
+    """evfly_conv2d_args (include/evfly_b200.h)."""
+    _fields_ = [("x", _vp), ("w", _vp), ("bias", _vp), ("post_scale", _vp), ("post_shift", _vp),
+                ("res", _vp), ("y", _vp),
+                ("N", _i32), ("Cin", _i32), ("H", _i32), ("W", _i32), ("Cout", _i32), ("KH", _i32),
+                ("KW", _i32), ("stride", _i32), ("pad", _i32), ("groups", _i32), ("act", _i32),
+                ("reserved", _i32),
+                ("xs", _i64 * 4), ("ys", _i64 * 4)]
+
+
+_p64 = C.POINTER(_i64)
+SIGNATURES.update({
+    "evfly_conv2d_f32": (_i32, [C.POINTER(ConvArgs), _vp]),
+    "evfly_pool2d_f32": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_resize_bilinear_f32": (_i32, [_vp, _p64, _vp, _p64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp]),
+    "evfly_layernorm_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "evfly_attention_small_f32": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_map4d_f32": (_i32, [_vp, _p64, _vp, _p64, _p64, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "evfly_pixel_shuffle_f32": (_i32, [_vp, _p64, _vp, _p64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_form_input_f32": (_i32, [_vp, _vp, _i64, _i64, _i32, _f32, _vp]),
+    "evfly_lstm_seq_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "evfly_convlstm_pointwise_f32": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "evfly_velpred_unit_f32": (_i32, [_vp, _vp, _i32, _vp]),
+})
+
+ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "gelu": 3, "tanh": 4, "sigmoid": 5}
+
 _lib = None
 
 
@@ -88,6 +117,15 @@ def ptr(t) -> int | None:
         raise EvflyError("libevfly_b200 takes device pointers only; got a CPU tensor")
     if not t.is_contiguous():
         raise EvflyError("libevfly_b200 takes contiguous tensors only")
+    return t.data_ptr()
+
+
+def ptr_any(t) -> int | None:
+    """data_ptr of a (possibly strided) CUDA view; the caller passes t.stride() alongside."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EvflyError("libevfly_b200 takes device pointers only; got a CPU tensor")
     return t.data_ptr()
 
 

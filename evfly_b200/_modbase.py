@@ -1,0 +1,109 @@
+"""Shared machinery of the drop-in nn.Modules: packed-weight caching and input plumbing."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class PackedModule(nn.Module):
+    """An nn.Module whose parameters are only CONTAINERS (so constructor, initialisation,
+    state_dict keys, .to(), .eval(), .parameters() behave exactly like the reference class) and
+    whose forward runs libevfly_b200 kernels on weights packed once per parameter version."""
+
+    def _weights_signature(self):
+        sig = []
+        for t in self.parameters(recurse=True):
+            sig.append((t.data_ptr(), t._version))
+        for t in self.buffers(recurse=True):
+            sig.append((t.data_ptr(), t._version))
+        return tuple(sig)
+
+    def packed(self):
+        sig = self._weights_signature()
+        cache = self.__dict__.get("_evfly_pack")
+        if cache is None or cache[0] != sig:
+            with torch.no_grad():
+                cache = (sig, self._pack())
+            self.__dict__["_evfly_pack"] = cache
+        return cache[1]
+
+    def _pack(self):  # -> anything; called under no_grad with parameters on their device
+        raise NotImplementedError
+
+    def _device(self) -> torch.device:
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise _lib.EvflyError(
+                f"{type(self).__name__} runs on a CUDA device only (B200, sm_100a); move it with .to('cuda'). "
+                "evfly_b200 has no CPU fallback.")
+        return p.device
+
+    def _check_inference(self):
+        if self.training and torch.is_grad_enabled():
+            raise _lib.EvflyError(
+                f"{type(self).__name__}: forward-only kernels. Call .eval() and run under torch.no_grad(), as every "
+                "inference call site of the reference does (run.py:261, run_competition.py:535, learner.py:755).")
+
+
+def to_dev(t, device):
+    """Host->device plumbing for inputs the callers hand over as CPU tensors."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def sn_effective_weight(lin: nn.Module) -> torch.Tensor:
+    """Eval-mode weight of an old-style spectral_norm-wrapped Linear: W_orig / (u^T W_orig v)
+    (SURVEY.md 8(b)); folded once at pack time."""
+    w = lin.weight_orig
+    sigma = torch.dot(lin.weight_u, torch.mv(w.reshape(w.shape[0], -1), lin.weight_v))
+    return (w / sigma).contiguous()
+
+
+def bn_affine(bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm as y = x*scale + shift."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    shift = bn.bias - bn.running_mean * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def pack_lstm(lstm: nn.LSTM):
+    """Per layer: (W_ih [4H,in], b_ih+b_hh or None, W_hh^T [H,4H])."""
+    layers = []
+    for l in range(lstm.num_layers):
+        w_ih = getattr(lstm, f"weight_ih_l{l}").contiguous()
+        w_hh_t = getattr(lstm, f"weight_hh_l{l}").t().contiguous()
+        b = None
+        if lstm.bias:
+            b = (getattr(lstm, f"bias_ih_l{l}") + getattr(lstm, f"bias_hh_l{l}")).contiguous()
+        layers.append((w_ih, b, w_hh_t))
+    return layers
+
+
+def run_lstm(ops, packed_layers, seq, state, hidden):
+    """nn.LSTM forward on an unbatched sequence seq [T,in] with state (h0,c0) [L,H] or None.
+    Returns (out [T,H], (h [L,H], c [L,H]))."""
+    L = len(packed_layers)
+    dev = seq.device
+    h_out = torch.empty((L, hidden), dtype=torch.float32, device=dev)
+    c_out = torch.empty((L, hidden), dtype=torch.float32, device=dev)
+    h0 = c0 = None
+    if state is not None:
+        h0, c0 = to_dev(state[0], dev), to_dev(state[1], dev)
+    lib = _lib.load()
+    inp = seq
+    for l, (w_ih, b, w_hh_t) in enumerate(packed_layers):
+        gx = ops.linear(inp, w_ih, b)
+        T = gx.shape[0]
+        hs = torch.empty((T, hidden), dtype=torch.float32, device=dev)
+        _lib.check(lib.evfly_lstm_seq_f32(_lib.ptr(gx), _lib.ptr(w_hh_t),
+                                          None if h0 is None else h0[l].data_ptr(),
+                                          None if c0 is None else c0[l].data_ptr(),
+                                          _lib.ptr(hs), h_out[l].data_ptr(), c_out[l].data_ptr(), T, hidden,
+                                          _lib.stream_ptr()), "evfly_lstm_seq_f32")
+        inp = hs
+    return inp, (h_out, c_out)

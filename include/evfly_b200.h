@@ -184,6 +184,104 @@ int evfly_quantile_scale_clip(const float* d_x, int N, int64_t elems_per_frame, 
                               float lo, float hi, float cutoff, float* d_out, float* d_q,
                               void* stream);
 
+/* ======================================================================================
+ * L3  model forward: operator entry points (fp32 exact path)
+ *
+ * The reference's forward is stock PyTorch (learner/learner_models.py:521-616,
+ * learner/vitfly_models.py:132-150, learner/ViTsubmodules.py:61-148,
+ * learner/ConvLSTM_pytorch/convlstm.py:38-53); there is no native interface to mirror, so the
+ * ABI exposes the operators those forwards are made of. The host-side drop-in nn.Modules
+ * (evfly_b200/learner_models.py ...) keep the reference's constructors, state_dict keys and
+ * forward() signatures and sequence these calls; they are capturable in a CUDA graph.
+ * Tensors are fp32; layouts are described by explicit element strides so that the
+ * reference's flatten/transpose/permute/cat glue costs no copies.
+ * ====================================================================================== */
+
+#define EVFLY_ACT_NONE     0
+#define EVFLY_ACT_RELU     1
+#define EVFLY_ACT_LEAKY    2   /* negative slope 0.01 (F.leaky_relu default)            */
+#define EVFLY_ACT_GELU     3   /* exact erf GELU (nn.GELU default)                       */
+#define EVFLY_ACT_TANH     4
+#define EVFLY_ACT_SIGMOID  5
+
+/* y = post_scale[c] * act(conv(x, w) + bias[c]) + post_shift[c] + res
+ * Direct convolution as an implicit GEMM (M = N*OH*OW pixels, N = Cout/groups, K = Cin/groups*KH*KW).
+ * x is addressed as x[n*xs[0] + c*xs[1] + h*xs[2] + w*xs[3]], y and res likewise with ys: a
+ * Linear layer over tokens [rows, K] is the 1x1 case with xs = {0, 1, 0, K}.
+ * w is PyTorch's [Cout, Cin/groups, KH, KW] contiguous. bias / post_* / res may be NULL.     */
+typedef struct evfly_conv2d_args {
+    const float* x;
+    const float* w;
+    const float* bias;
+    const float* post_scale;
+    const float* post_shift;
+    const float* res;
+    float*       y;
+    int32_t N, Cin, H, W, Cout, KH, KW, stride, pad, groups, act, reserved;
+    int64_t xs[4];
+    int64_t ys[4];
+} evfly_conv2d_args;
+int evfly_conv2d_f32(const evfly_conv2d_args* args, void* stream);
+
+/* 2-D pooling without padding, floor mode, on contiguous [planes,H,W] -> [planes,OH,OW].
+ * mode 0 = max, 1 = average. negate_in computes pool(-x) (the reference's min-pool idiom,
+ * vitfly_models.py:58 / learner_models.py:76-93), negate_out negates the result.            */
+int evfly_pool2d_f32(const float* d_x, float* d_y, int64_t planes, int H, int W, int k, int stride,
+                     int mode, int negate_in, int negate_out, void* stream);
+
+/* Bilinear resize (F.interpolate / nn.Upsample) of x[n*xs[0]+c*xs[1]+h*xs[2]+w*xs[3]]
+ * ([N,C,H,W]) to OHxOW, written to y[n*ys[0]+c*ys[1]+oh*ys[2]+ow*ys[3]] (so it can land inside
+ * a concat buffer), then y = clip(y*mul + add, lo, hi) (mul=1, add=0, lo=-inf, hi=+inf for a
+ * plain resize).                                                                             */
+int evfly_resize_bilinear_f32(const float* d_x, const int64_t* xs, float* d_y, const int64_t* ys,
+                              int N, int C, int H, int W, int OH, int OW, int align_corners,
+                              float mul, float add, float lo, float hi, void* stream);
+
+/* nn.LayerNorm over the last dimension of contiguous [rows, C] (C <= 1024), eps inside sqrt. */
+int evfly_layernorm_f32(const float* d_x, const float* d_gamma, const float* d_beta, float* d_y,
+                        int64_t rows, int C, float eps, void* stream);
+
+/* softmax(q k^T / sqrt(C/heads)) v with a handful of keys (spatial-reduction attention,
+ * ViTsubmodules.py:74-80): q [B,N,C], kv [B,n_kv,2C] laid out [key|value][head][d], out [B,N,C].
+ * n_kv <= 32.                                                                               */
+int evfly_attention_small_f32(const float* d_q, const float* d_kv, float* d_out, int B, int N,
+                              int C, int heads, int n_kv, void* stream);
+
+/* Strided 4-D elementwise map: y[idx.ys] = clip(x[idx.xs]*mul/div + add, lo, hi) over
+ * dims[4]. Serves the crop-skip copy (learner_models.py:512), clip(depth*2,0,1) (:634), the
+ * metadata concat desvel/10, desvel*0.1, quat (vitfly_models.py:144,65) and plain copies.
+ * `div` keeps x/10 and x*0.1 distinct in fp32, as the reference has both.                    */
+int evfly_map4d_f32(const float* d_x, const int64_t* xs, float* d_y, const int64_t* ys,
+                    const int64_t* dims, float mul, float div, float add, float lo, float hi,
+                    void* stream);
+
+/* nn.PixelShuffle(r) of x ([N, C*r*r, H, W], strides xs) into y ([N,C,H*r,W*r], strides ys).   */
+int evfly_pixel_shuffle_f32(const float* d_x, const int64_t* xs, float* d_y, const int64_t* ys,
+                            int N, int C, int H, int W, int r, void* stream);
+
+/* OrigUNet.form_input (learner_models.py:476-494): IN PLACE x[|x| < cutoff] = 0 on the caller's
+ * frames [N,1,H,W] (the reference mutates its input too), then
+ *   form_bev 0: out [N,2,H,W], BOTH channels = max(x,0) (the reference's expand() aliasing),
+ *   form_bev 1: out = |x|,   form_bev 2: out = (x != 0) ? 1 : 0  (NaN != 0 -> 1).   */
+int evfly_form_input_f32(float* d_x, float* d_out, int64_t n, int64_t plane, int form_bev,
+                         float cutoff, void* stream);
+
+/* nn.LSTM over an UNBATCHED sequence (the reference feeds [N,feat], so N is time): one layer.
+ * d_gx [T,4H] = x_t W_ih^T + b_ih + b_hh (a conv2d_f32 call), gate order i,f,g,o;
+ * d_whh_t [H,4H] = W_hh transposed; d_h0/d_c0 [H] (NULL = zeros); d_hs [T,H] receives every h_t;
+ * d_hT/d_cT [H] the final state. One persistent CTA walks the T steps with h,c in shared memory. */
+int evfly_lstm_seq_f32(const float* d_gx, const float* d_whh_t, const float* d_h0, const float* d_c0,
+                       float* d_hs, float* d_hT, float* d_cT, int T, int H, void* stream);
+
+/* ConvLSTM cell pointwise (convlstm.py:44-53), gate order i,f,o,g: gates [4*Ch, P],
+ * c [Ch,P] updated in place, h_out [Ch,P]:  c = sig(f)*c + sig(i)*tanh(g);  h = sig(o)*tanh(c).  */
+int evfly_convlstm_pointwise_f32(const float* d_gates, float* d_c, float* d_h_out, int Ch, int P,
+                                 void* stream);
+
+/* VelPredictor num_out=1 tail (learner_models.py:321-333): y [N,1] -> out [N,3] =
+ * [sqrt(clip(1-y^2,0,1)), y, 0].                                                             */
+int evfly_velpred_unit_f32(const float* d_y, float* d_out, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
