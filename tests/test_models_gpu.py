@@ -13,7 +13,13 @@ from oracle.synth_ckpt import synth_state_dict, synthetic_depth, synthetic_frame
 from tests.test_models_cpu import build
 
 pytestmark = pytest.mark.gpu
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
+
 RTOL, ATOL = 1e-5, 1e-5
 
 

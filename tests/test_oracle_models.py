@@ -10,7 +10,13 @@ import torch
 from oracle import model_oracle as M
 from oracle.synth_ckpt import synth_state_dict, synthetic_depth, synthetic_frames
 
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
+
 RTOL, ATOL = 1e-5, 2e-6      # fp32 re-association noise between two CPU op orders
 
 
