@@ -1,0 +1,444 @@
+// tc_conv_bf16.cu -- L3 fast path: bf16 implicit-GEMM convolution on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands staged by TMA with 128B/64B swizzle).
+//
+// Replaces the 3x3 valid convolutions, 1x1 convolutions and 2x2-stride-2 transposed
+// convolutions of OrigUNet (learner/learner_models.py:373-414, 533-583) and the ConvLSTM gate
+// convolution (learner/ConvLSTM_pytorch/convlstm.py:42), i.e. ~97 % of the model's FLOPs.
+//
+// Layout: activations are bf16 NHWC on a PITCH-PRESERVING grid: a level's tensors all keep the
+// level's input height x width as their row pitch, and a valid conv only shrinks the VALID extent
+// (the last rows/cols of the grid hold don't-care values). On such a grid
+//     out[m, :] = sum_{kh,kw} in[m + kh*Wp + kw, :] * W[kh,kw]          (m = flattened n,h,w)
+// so a 3x3 valid conv is 9 shifted GEMMs accumulated in TMEM, and the A tile of every tap is a
+// plain 2-D TMA box [128 pixels x KC channels] at row m0 + kh*Wp + kw (rows past the end are
+// zero-filled by TMA). Valid outputs only ever read valid inputs, so the don't-care border never
+// leaks. 2x2 max-pool compacts the valid region into the next level's grid.
+//
+// Kernel anatomy (one CTA = 256 threads, persistent over output tiles):
+//   warp 0 lane 0 : TMA producer  (A box + B box per K-block -> smem ring, mbarrier expect_tx)
+//   warp 1 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::f16, M=128, N=TN, K=16)
+//   warp 2        : TMEM allocator (2 accumulator buffers of TN fp32 columns)
+//   warps 4..7    : epilogue      (tcgen05.ld 32x32b -> +bias -> ReLU -> bf16 -> 16-byte stores)
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace evfly {
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand, rows at (swizzle) byte pitch, 8-row atoms SBO bytes apart
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset | [61,64) layout
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)((smem_addr >> 7) & 0x7u) << 49;  // 0 for 1024-byte aligned stage buffers
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw64 = 4;
+
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------
+struct TcArgs {
+    const float* bias;     // fp32 [bias_len] or nullptr; indexed by (n % bias_mod)
+    const float* res;      // fp32 [M_rows, n_rows] or nullptr, added before the activation
+    __nv_bfloat16* out;    // bf16 destination
+    float* out_f32;        // optional fp32 destination instead (same addressing)
+    long long M_rows;      // rows of the source pitch grid
+    int Cin, n_rows;       // K per tap; GEMM N (rows of the weight matrix)
+    int taps, w_pitch;     // 1 or 9; pixels per grid row (the kh shift)
+    int relu;
+    long long out_ld;      // elements per destination pixel
+    int out_c0;            // channel offset inside the destination pixel (concat)
+    int bias_mod;
+    // transposed-conv scatter: GEMM column n = phase*cout_t + co, phase = 2a+b
+    int convt, Hp, Wp, valid_h, valid_w, cout_t;
+};
+
+template <int TN, int KC>
+struct TcCfg {
+    static constexpr int BM = 128;
+    static constexpr int A_BYTES = BM * KC * 2;
+    static constexpr int B_BYTES = TN * KC * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (STAGE_BYTES * 6 <= 200 * 1024) ? 6 : (STAGE_BYTES * 4 <= 200 * 1024 ? 4 : 3);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = (2 * TN <= 32) ? 32 : (2 * TN <= 64 ? 64 : (2 * TN <= 128 ? 128 : (2 * TN <= 256 ? 256 : 512)));
+    static constexpr uint32_t LAYOUT = (KC == 64) ? kLayoutSw128 : kLayoutSw64;
+    static constexpr uint32_t SBO = 8 * KC * 2;  // 8 rows x row bytes
+};
+
+template <int TN, int KC>
+__global__ void __launch_bounds__(256, 1)
+k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs p) {
+    using Cfg = TcCfg<TN, KC>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]
+    uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]
+    uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m_tiles = (p.M_rows + Cfg::BM - 1) / Cfg::BM;
+    const int n_tiles = (p.n_rows + TN - 1) / TN;
+    const long long total_tiles = m_tiles * n_tiles;
+    const int kc_per_tap = p.Cin / KC;
+    const int k_blocks = p.taps * kc_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const long long mt = tile / n_tiles;
+            const int nt = (int)(tile - mt * n_tiles);
+            const long long m0 = mt * Cfg::BM;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+                const int kh = tap / 3, kw = tap - kh * 3;  // taps == 1 -> 0,0
+                const long long row = m0 + (long long)kh * p.w_pitch + kw;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                uint8_t* sb = sa + Cfg::A_BYTES;
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_2d(sa, &map_a, &full_bar[stage], kc * KC, (int)row);
+                tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * KC, nt * TN);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, TN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TN);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                    const uint64_t da = make_smem_desc(sa + k * 32, Cfg::SBO, Cfg::LAYOUT);
+                    const uint64_t db = make_smem_desc(sb + k * 32, Cfg::SBO, Cfg::LAYOUT);
+                    umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const long long mt = tile / n_tiles;
+            const int nt = (int)(tile - mt * n_tiles);
+            const long long m = mt * Cfg::BM + ew * 32 + lane;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            // destination pixel of this row
+            bool row_ok = m < p.M_rows;
+            long long dst_pix = m;
+            int ih = 0, iw = 0;
+            long long img = 0;
+            if (p.convt) {
+                const long long hw = (long long)p.Hp * p.Wp;
+                img = m / hw;
+                const int rem = (int)(m - img * hw);
+                ih = rem / p.Wp;
+                iw = rem - ih * p.Wp;
+                row_ok = row_ok && ih < p.valid_h && iw < p.valid_w;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN + c0), r);
+                tmem_ld_wait();
+                const int n_first = nt * TN + c0;
+                if (row_ok && n_first < p.n_rows) {
+                    int ch0 = n_first;
+                    if (p.convt) {
+                        const int phs = n_first / p.cout_t;  // a 32-column slab never straddles a phase (cout_t % 32 == 0)
+                        ch0 = n_first - phs * p.cout_t;
+                        const int a = phs >> 1, b = phs & 1;
+                        dst_pix = (img * (2 * p.valid_h) + 2 * ih + a) * (long long)(2 * p.valid_w) + 2 * iw + b;
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(r[j]);
+                        if (p.bias) x += __ldg(p.bias + (n_first + j) % p.bias_mod);
+                        if (p.res && n_first + j < p.n_rows) x += p.res[m * (long long)p.n_rows + n_first + j];
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        v[j] = x;
+                    }
+                    const int ncols = min(32, p.n_rows - n_first);
+                    if (p.out_f32) {
+                        float* o = p.out_f32 + dst_pix * p.out_ld + p.out_c0 + ch0;
+                        for (int j = 0; j < ncols; ++j) o[j] = v[j];
+                    } else {
+                        __nv_bfloat16* o = p.out + dst_pix * p.out_ld + p.out_c0 + ch0;
+                        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 pk;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
+                                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
+                                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                                pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                                pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                                reinterpret_cast<uint4*>(o)[q] = pk;
+                            }
+                        } else {
+                            for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (cols contiguous, row pitch ld elements), box [box_rows x box_cols]
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                       uint32_t box_cols) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return EVFLY_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = (box_cols * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols);
+        return EVFLY_ERR_CUDA;
+    }
+    return EVFLY_OK;
+}
+
+template <int TN, int KC>
+static int launch_tc(const evfly_tc_conv_args& a, const TcArgs& p, cudaStream_t st) {
+    using Cfg = TcCfg<TN, KC>;
+    CUtensorMap map_a, map_b;
+    int rc = make_map_2d(&map_a, a.x, (uint64_t)a.M_rows, (uint64_t)a.Cin, (uint64_t)a.Cin, Cfg::BM, KC);
+    if (rc) return rc;
+    rc = make_map_2d(&map_b, a.w, (uint64_t)a.n_rows, (uint64_t)a.taps * a.Cin, (uint64_t)a.taps * a.Cin, TN, KC);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv_bf16<TN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long tiles = ceil_div(a.M_rows, Cfg::BM) * ceil_div(a.n_rows, TN);
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    k_tc_conv_bf16<TN, KC><<<grid, 256, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+}  // namespace evfly
+
+using namespace evfly;
+
+extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) {
+    EVFLY_REQUIRE(args, "tc_conv_bf16: null args");
+    const evfly_tc_conv_args a = *args;
+    EVFLY_REQUIRE(a.x && a.w && (a.out || a.out_f32), "tc_conv_bf16: null tensor");
+    EVFLY_REQUIRE(a.M_rows > 0 && a.M_rows < (1ll << 31) && a.Cin > 0 && a.n_rows > 0, "tc_conv_bf16: bad shape");
+    EVFLY_REQUIRE(a.taps == 1 || a.taps == 9, "tc_conv_bf16: taps must be 1 or 9");
+    EVFLY_REQUIRE(a.Cin % 32 == 0, "tc_conv_bf16: Cin must be a multiple of 32 (got %d)", a.Cin);
+    EVFLY_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0, "tc_conv_bf16: operands must be 16-byte aligned");
+    EVFLY_REQUIRE(!(a.convt && a.res_f32), "tc_conv_bf16: res_f32 is not supported with convt");
+    EVFLY_REQUIRE(!a.convt || (a.taps == 1 && a.cout_t % 32 == 0 && a.n_rows == 4 * a.cout_t && a.Hp > 0 && a.Wp > 0 && a.valid_h <= a.Hp && a.valid_w <= a.Wp),
+                  "tc_conv_bf16: bad transposed-conv arguments");
+    TcArgs p;
+    p.bias = a.bias;
+    p.res = a.res_f32;
+    p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+    p.out_f32 = a.out_f32;
+    p.M_rows = a.M_rows;
+    p.Cin = a.Cin;
+    p.n_rows = a.n_rows;
+    p.taps = a.taps;
+    p.w_pitch = a.w_pitch;
+    p.relu = a.relu;
+    p.out_ld = a.out_ld;
+    p.out_c0 = a.out_c0;
+    p.bias_mod = a.convt ? a.cout_t : a.n_rows;
+    p.convt = a.convt;
+    p.Hp = a.Hp;
+    p.Wp = a.Wp;
+    p.valid_h = a.valid_h;
+    p.valid_w = a.valid_w;
+    p.cout_t = a.cout_t;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool kc64 = (a.Cin % 64 == 0);
+    // N tile: the whole weight matrix when it fits 256 accumulator columns, else 256-wide tiles
+    const int n = a.n_rows;
+    if (kc64) {
+        if (n <= 32) return launch_tc<32, 64>(a, p, st);
+        if (n <= 64) return launch_tc<64, 64>(a, p, st);
+        if (n <= 128) return launch_tc<128, 64>(a, p, st);
+        return launch_tc<256, 64>(a, p, st);
+    } else {
+        if (n <= 32) return launch_tc<32, 32>(a, p, st);
+        if (n <= 64) return launch_tc<64, 32>(a, p, st);
+        if (n <= 128) return launch_tc<128, 32>(a, p, st);
+        return launch_tc<256, 32>(a, p, st);
+    }
+}

@@ -1,0 +1,80 @@
+"""The hot path end to end on one GPU: packed event records of consecutive windows ->
+count frames (+ temporal voxel grid) -> decode/crop -> 97th-percentile scale + clip ->
+OrigUNet_w_VITFLY_ViTLSTM forward with carried recurrent state.
+
+Mirrors what evfly_ros/run.py does per timer tick (evs_process :330-364 + run_model :245-282)
+and what learner/evaluation_tools.py does per trajectory (:62-66), with the C++ node's
+accumulation (evfly_ros/src/node.cpp) folded in front.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .events import L1
+
+
+class PerceptionPipeline:
+    def __init__(self, model, sensor_hw=(480, 640), model_hw=(260, 346), num_bins=5, desvel=4.0, device=None):
+        self.model = model
+        self.H, self.W = sensor_hw
+        self.h, self.w = model_hw
+        self.B = num_bins
+        self.desvel = float(desvel)
+        self.dev = next(model.parameters()).device if device is None else torch.device(device)
+        if self.dev.type != "cuda":
+            raise _lib.EvflyError("PerceptionPipeline needs the model on a CUDA device")
+        self.state_unet = None
+        self.state_vit = None
+
+    def reset(self):
+        self.state_unet = self.state_vit = None
+
+    # ---- L1 + L2 ---------------------------------------------------------------------------------
+    def frames_from_windows(self, records, edges_ns, want_voxel=True, sorted_by_time=True):
+        """records uint8 [n,16] on the device, edges_ns int64 [T+1] on the device.
+        Returns (frames fp32 [T,1,h,w] normalised like run.py:250-253, counts, voxel)."""
+        lib = _lib.load()
+        T = edges_ns.shape[0] - 1
+        counts, voxel = L1.accumulate_windows(records, edges_ns, self.H, self.W, self.B if want_voxel else None,
+                                              sorted_by_time=sorted_by_time)
+        frames = torch.empty((T, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
+        st = _lib.stream_ptr()
+        _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), T, self.H, self.W, self.h, self.w, 0.2,
+                                         _lib.ptr(frames), st), "evfly_decode_crop")
+        _lib.check(lib.evfly_quantile_scale_clip(_lib.ptr(frames), T, self.h * self.w, 0.97, -1.0, 1.0, 0.0,
+                                                 _lib.ptr(frames), None, st), "evfly_quantile_scale_clip")
+        return frames, counts, voxel
+
+    # ---- L3 ----------------------------------------------------------------------------------------
+    def forward(self, frames, carry_state=True):
+        """frames [T,1,h,w] = one sequence of T consecutive windows. Returns (vel [T,3], depth)."""
+        T = frames.shape[0]
+        desvel = torch.full((T, 1), self.desvel, dtype=torch.float32, device=self.dev)
+        vel, (depth, _, ((hu, _), hv)) = self.model([frames, desvel, [self.state_unet, None], self.state_vit])
+        if carry_state:
+            self.state_unet, self.state_vit = hu, hv
+        return vel, depth
+
+    def __call__(self, records, edges_ns, want_voxel=True):
+        frames, counts, voxel = self.frames_from_windows(records, edges_ns, want_voxel)
+        vel, depth = self.forward(frames)
+        return vel, depth, counts, voxel
+
+
+def build_deployed_model(device="cuda", seed_state_dict=None, logger=None):
+    """OrigUNet_w_VITFLY_ViTLSTM in the shipped configuration (learner/configs/eval_config_real.txt:39-47:
+    bev=2, skip_type=interp, num_recurrent=[1,0], resize_input=[260,346], velpred=0)."""
+    from .learner_models import OrigUNet_w_VITFLY_ViTLSTM
+    quiet = logger if logger is not None else (lambda *a, **k: None)
+    enc = dict(num_layers=2, kernel_sizes=[5, 3], kernel_strides=[2, 2], out_channels=[8, 32], activations=["relu", "relu"],
+               pool_type="max", invert_pool_inputs=True, pool_kernels=[2, 2], pool_strides=[2, 2], conv_function="conv2d")
+    fc = dict(num_layers=4, layer_sizes=[1024, 128, 16, 1], activations=["leaky_relu"] * 3 + ["tanh"], dropout_p=0.1)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = OrigUNet_w_VITFLY_ViTLSTM(num_in_channels=2, num_out_channels=1, num_recurrent=[1, 0], input_shape=[1, 1, 260, 346],
+                                      logger=quiet, velpred=0, enc_params=enc, fc_params=fc, form_BEV=2, evs_min_cutoff=1e-3,
+                                      skip_type="interp", is_deployment=False)
+    if seed_state_dict is not None:
+        m.load_state_dict(seed_state_dict, strict=True)
+    return m.to(device).eval().float()

@@ -1,0 +1,158 @@
+"""Typed wrappers of the bf16 tensor-core entry points (include/evfly_b200.h, bf16 section).
+
+A `Grid` is a bf16 NHWC activation on a pitch-preserving grid: data [N, Hp, Wp, C] plus the valid
+extent (vh, vw). See evfly_b200/csrc/tc_conv_bf16.cu for why this layout turns a 3x3 valid conv
+into nine shifted GEMMs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class Grid:
+    data: torch.Tensor   # bf16 [N, Hp, Wp, C] contiguous
+    vh: int
+    vw: int
+
+    @property
+    def N(self): return self.data.shape[0]
+    @property
+    def Hp(self): return self.data.shape[1]
+    @property
+    def Wp(self): return self.data.shape[2]
+    @property
+    def C(self): return self.data.shape[3]
+    @property
+    def rows(self): return self.data.shape[0] * self.data.shape[1] * self.data.shape[2]
+
+
+def new_grid(N, Hp, Wp, Cc, vh, vw, device) -> Grid:
+    return Grid(torch.empty((N, Hp, Wp, Cc), dtype=BF16, device=device), vh, vw)
+
+
+def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] fp32 -> bf16 [Cout, 9*Cin] with K index = tap*Cin + ci (tap = kh*3+kw)."""
+    Cout, Cin = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(BF16).contiguous()
+
+
+def pack_conv1x1_weight(w: torch.Tensor) -> torch.Tensor:
+    return w.reshape(w.shape[0], -1).to(BF16).contiguous()
+
+
+def pack_convt2x2_weight(w: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d weight [Cin, Cout, 2, 2] -> bf16 [4*Cout, Cin], row = (2a+b)*Cout + co."""
+    Cin, Cout = w.shape[:2]
+    return w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(BF16).contiguous()
+
+
+def _call(a: _lib.TcConvArgs):
+    _lib.check(_lib.load().evfly_tc_conv_bf16(C.byref(a), _lib.stream_ptr()), "evfly_tc_conv_bf16")
+
+
+def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None) -> Grid:
+    """3x3 valid conv (+bias, ReLU) on the grid; the result keeps the pitch, valid extent - 2."""
+    Cout = w_packed.shape[0]
+    if out is None:
+        out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
+    a = _lib.TcConvArgs()
+    a.x, a.w, a.bias, a.out = g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr()
+    a.M_rows, a.out_ld = g.rows, Cout
+    a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = g.C, Cout, 9, g.Wp, int(relu), 0
+    _call(a)
+    return out
+
+
+def gemm(x2d, w_packed, bias=None, relu=False, out2d=None, out_f32=None, res_f32=None):
+    """[M, K] bf16 @ [N, K]^T -> bf16 [M, N] (or fp32 when out_f32 is given); res_f32 [M, N] added."""
+    M, K = x2d.shape
+    Nn = w_packed.shape[0]
+    assert x2d.is_contiguous() and x2d.dtype == BF16 and w_packed.shape[1] == K
+    a = _lib.TcConvArgs()
+    a.x, a.w, a.bias = x2d.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias)
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+        a.out_f32 = out_f32.data_ptr()
+        ret = out_f32
+    else:
+        if out2d is None:
+            out2d = torch.empty((M, Nn), dtype=BF16, device=x2d.device)
+        a.out = out2d.data_ptr()
+        ret = out2d
+    a.res_f32 = None if res_f32 is None else res_f32.data_ptr()
+    a.M_rows, a.out_ld = M, Nn
+    a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = K, Nn, 1, 0, int(relu), 0
+    _call(a)
+    return ret
+
+
+def conv_transpose2x2(g: Grid, w_packed, bias, out_data: torch.Tensor, out_c0: int):
+    """ConvTranspose2d(k=2,s=2) of the valid region into channels [out_c0, out_c0+Cout) of the
+    compact grid out_data [N, 2*vh, 2*vw, Ctot]."""
+    Cout = w_packed.shape[0] // 4
+    assert tuple(out_data.shape[:3]) == (g.N, 2 * g.vh, 2 * g.vw)
+    a = _lib.TcConvArgs()
+    a.x, a.w, a.bias, a.out = g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out_data.data_ptr()
+    a.M_rows, a.out_ld = g.rows, out_data.shape[3]
+    a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = g.C, 4 * Cout, 1, 0, 0, out_c0
+    a.convt, a.Hp, a.Wp, a.valid_h, a.valid_w, a.cout_t = 1, g.Hp, g.Wp, g.vh, g.vw, Cout
+    _call(a)
+
+
+def stem_conv3x3(x_nchw_f32, w, bias) -> Grid:
+    N, Cin, H, W = x_nchw_f32.shape
+    out = new_grid(N, H, W, 32, H - 2, W - 2, x_nchw_f32.device)
+    _lib.check(_lib.load().evfly_stem_conv3x3_bf16(_lib.ptr(x_nchw_f32), _lib.ptr(w), _lib.ptr(bias), out.data.data_ptr(),
+                                                    N, Cin, H, W, _lib.stream_ptr()), "evfly_stem_conv3x3_bf16")
+    return out
+
+
+def maxpool2x2(g: Grid) -> Grid:
+    out = new_grid(g.N, g.vh // 2, g.vw // 2, g.C, g.vh // 2, g.vw // 2, g.data.device)
+    _lib.check(_lib.load().evfly_maxpool2x2_nhwc_bf16(g.data.data_ptr(), out.data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C,
+                                                       _lib.stream_ptr()), "evfly_maxpool2x2_nhwc_bf16")
+    return out
+
+
+def resize_bilinear_into(g: Grid, OH, OW, out_data, out_c0):
+    assert tuple(out_data.shape[:3]) == (g.N, OH, OW)
+    _lib.check(_lib.load().evfly_resize_bilinear_nhwc_bf16(g.data.data_ptr(), out_data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C,
+                                                            OH, OW, out_data.shape[3], out_c0, _lib.stream_ptr()),
+               "evfly_resize_bilinear_nhwc_bf16")
+
+
+def crop_into(g: Grid, h0, w0, OH, OW, out_data, out_c0):
+    assert tuple(out_data.shape[:3]) == (g.N, OH, OW)
+    _lib.check(_lib.load().evfly_crop_nhwc_bf16(g.data.data_ptr(), out_data.data_ptr(), g.N, g.Hp, g.Wp, g.C, h0, w0, OH, OW,
+                                                 out_data.shape[3], out_c0, _lib.stream_ptr()), "evfly_crop_nhwc_bf16")
+
+
+def convlstm_pointwise(gates_f32, c_f32, h_bf16):
+    P, Ch = c_f32.shape
+    _lib.check(_lib.load().evfly_convlstm_pointwise_nhwc(_lib.ptr(gates_f32), _lib.ptr(c_f32), h_bf16.data_ptr(), P, Ch,
+                                                          _lib.stream_ptr()), "evfly_convlstm_pointwise_nhwc")
+
+
+def nchw_to_grid(x_f32, Hp, Wp) -> Grid:
+    N, Cc, vh, vw = x_f32.shape
+    out = new_grid(N, Hp, Wp, Cc, vh, vw, x_f32.device)
+    _lib.check(_lib.load().evfly_nchw_f32_to_nhwc_bf16(_lib.ptr(x_f32.contiguous()), out.data.data_ptr(), N, Cc, vh, vw, Hp, Wp,
+                                                        _lib.stream_ptr()), "evfly_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def grid_to_nchw(data, vh, vw) -> torch.Tensor:
+    """bf16 or fp32 [N,Hp,Wp,C] -> fp32 NCHW [N,C,vh,vw]."""
+    N, Hp, Wp, Cc = data.shape
+    out = torch.empty((N, Cc, vh, vw), dtype=torch.float32, device=data.device)
+    _lib.check(_lib.load().evfly_nhwc_to_nchw_f32(data.data_ptr(), int(data.dtype == torch.float32), _lib.ptr(out), N, Cc, vh, vw,
+                                                   Hp, Wp, _lib.stream_ptr()), "evfly_nhwc_to_nchw_f32")
+    return out

@@ -282,6 +282,74 @@ int evfly_convlstm_pointwise_f32(const float* d_gates, float* d_c, float* d_h_ou
  * [sqrt(clip(1-y^2,0,1)), y, 0].                                                             */
 int evfly_velpred_unit_f32(const float* d_y, float* d_out, int N, void* stream);
 
+/* ======================================================================================
+ * L3  model forward: bf16 tensor-core path (tcgen05 / TMEM / TMA)
+ *
+ * Activations are bf16 NHWC on a pitch-preserving grid [N, Hp, Wp, C]: every tensor of a UNet
+ * level keeps the level's input Hp x Wp as its pitch and a valid 3x3 conv only shrinks the VALID
+ * extent (vh x vw); positions outside it hold don't-care values that no valid output ever reads.
+ * On that grid a 3x3 valid conv is out[m] = sum_taps in[m + kh*Wp + kw] W[tap]: nine shifted GEMMs
+ * accumulated in TMEM (see evfly_b200/csrc/tc_conv_bf16.cu).
+ * ====================================================================================== */
+
+/* out[dst(m), c0 + n] = relu?( sum_{tap,k} x[m + shift(tap), k] * w[n, tap*Cin + k] + bias[n] + res[m, n] )
+ *   x   bf16 [M_rows, Cin]            (the flattened pitch grid)
+ *   w   bf16 [n_rows, taps*Cin]       ([Cout][tap][Cin] for a conv; [4][Cout][Cin] for convt)
+ *   taps 9: shift = kh*w_pitch + kw (3x3 valid conv);  taps 1: plain GEMM (1x1 conv / Linear)
+ *   out bf16 (or out_f32) with out_ld elements per destination pixel, channel offset out_c0
+ *   res_f32: optional fp32 [M_rows, n_rows] added before the activation (ConvLSTM x-gates)
+ *   convt = 1: ConvTranspose2d(k=2,s=2): GEMM column n = (2a+b)*cout_t + co goes to destination
+ *              pixel (img, 2*ih+a, 2*iw+b) of the compact grid [N, 2*valid_h, 2*valid_w]; rows of
+ *              the source grid [N,Hp,Wp] outside valid_h x valid_w are skipped.
+ * Cin must be a multiple of 32.                                                              */
+typedef struct evfly_tc_conv_args {
+    const void*  x;
+    const void*  w;
+    const float* bias;
+    const float* res_f32;
+    void*        out;
+    float*       out_f32;
+    int64_t M_rows;
+    int64_t out_ld;
+    int32_t Cin, n_rows, taps, w_pitch, relu, out_c0;
+    int32_t convt, Hp, Wp, valid_h, valid_w, cout_t;
+} evfly_tc_conv_args;
+int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream);
+
+/* First UNet layer (Cin = 1 or 2, so K = 9 or 18: CUDA cores): fp32 NCHW [N,Cin,H,W] -> 3x3 valid
+ * conv + bias + ReLU -> bf16 NHWC [N,H,W,32] on the input's own grid (valid (H-2)x(W-2)).
+ * w fp32 [32,Cin,3,3] (PyTorch layout), bias fp32 [32].                                       */
+int evfly_stem_conv3x3_bf16(const float* d_x, const float* d_w, const float* d_bias, void* d_out,
+                            int N, int Cin, int H, int W, void* stream);
+
+/* 2x2 stride-2 max-pool of the valid region of a bf16 NHWC pitch grid [N,Hp,Wp,C] (valid vh x vw)
+ * into a compact grid [N, vh/2, vw/2, C]. C % 8 == 0.                                         */
+int evfly_maxpool2x2_nhwc_bf16(const void* d_x, void* d_y, int N, int Hp, int Wp, int vh, int vw, int C,
+                               void* stream);
+
+/* Bilinear resize (align_corners=False) of the valid region of a bf16 NHWC pitch grid to OHxOW,
+ * written as bf16 to y[(n*OH+oh)*OW+ow][c0 + c] with out_ld elements per pixel (the `interp` skip
+ * connection landing in its half of the decoder's concat buffer). C % 8 == 0.                 */
+int evfly_resize_bilinear_nhwc_bf16(const void* d_x, void* d_y, int N, int Hp, int Wp, int vh, int vw,
+                                    int C, int OH, int OW, int64_t out_ld, int out_c0, void* stream);
+
+/* Copy (crop) of a window of the valid region: y[(n*OH+oh)*OW+ow][c0+c] = x[n, h0+oh, w0+ow, c].  */
+int evfly_crop_nhwc_bf16(const void* d_x, void* d_y, int N, int Hp, int Wp, int C, int h0, int w0, int OH,
+                         int OW, int64_t out_ld, int out_c0, void* stream);
+
+/* ConvLSTM cell update on the pitch grid: gates fp32 [P, 4*Ch] pixel-major, gate order i,f,o,g;
+ * c fp32 [P,Ch] in place; h written as bf16 [P,Ch] (next step's GEMM operand + decoder input).  */
+int evfly_convlstm_pointwise_nhwc(const float* d_gates, float* d_c, void* d_h_bf16, int64_t P, int Ch,
+                                  void* stream);
+
+/* fp32 <-> bf16 layout converters between the reference's NCHW tensors and the pitch grids:
+ * to_nhwc: x fp32 NCHW [N,C,vh,vw] -> bf16 [N,Hp,Wp,C] (positions outside vh x vw zeroed);
+ * to_nchw: bf16 or fp32 (src_is_f32) pitch grid -> fp32 NCHW [N,C,vh,vw].                      */
+int evfly_nchw_f32_to_nhwc_bf16(const float* d_x, void* d_y, int N, int C, int vh, int vw, int Hp, int Wp,
+                                void* stream);
+int evfly_nhwc_to_nchw_f32(const void* d_x, int src_is_f32, float* d_y, int N, int C, int vh, int vw, int Hp,
+                           int Wp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
