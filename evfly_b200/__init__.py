@@ -7,3 +7,14 @@ kernels reached through the C ABI of libevfly_b200.so (include/evfly_b200.h); th
 fallback. See DESIGN.md and INTEGRATION.md.
 """
 __version__ = "0.1.0"
+
+
+def set_precision(model, precision: str):
+    """'fp32': exact CUDA-core path (matches the reference within rtol 1e-5, the default);
+    'bf16': tcgen05 tensor-core path (rtol 1e-2). Applies to every sub-module that has both."""
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    for m in model.modules():
+        if hasattr(type(m), "precision"):
+            m.precision = precision
+    return model

@@ -147,8 +147,10 @@ struct TcCfg {
     static constexpr int B_BYTES = TN * KC * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (STAGE_BYTES * 6 <= 200 * 1024) ? 6 : (STAGE_BYTES * 4 <= 200 * 1024 ? 4 : 3);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = (2 * TN <= 32) ? 32 : (2 * TN <= 64 ? 64 : (2 * TN <= 128 ? 128 : (2 * TN <= 256 ? 256 : 512)));
+    static constexpr int NACC = (TN <= 64) ? 4 : 2;            // TMEM accumulator buffers
+    static constexpr int BIAS_FLOATS = 2048;                   // bias of every GEMM column, staged once per CTA
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_FLOATS * 4;
+    static constexpr int TMEM_COLS = (NACC * TN <= 32) ? 32 : (NACC * TN <= 64 ? 64 : (NACC * TN <= 128 ? 128 : (NACC * TN <= 256 ? 256 : 512)));
     static constexpr uint32_t LAYOUT = (KC == 64) ? kLayoutSw128 : kLayoutSw64;
     static constexpr uint32_t SBO = 8 * KC * 2;  // 8 rows x row bytes
 };
@@ -162,9 +164,10 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
     uint64_t* full_bar = bars;                       // [STAGES]
     uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
-    uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]
-    uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+    uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;                 // [NACC]
+    uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + Cfg::NACC;    // [NACC]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 2 * Cfg::NACC);
+    float* s_bias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m_tiles = (p.M_rows + Cfg::BM - 1) / Cfg::BM;
@@ -182,13 +185,18 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < Cfg::NACC; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    {   // bias of GEMM column n (zero when absent / past the end): broadcast reads in the epilogue
+        const int n_pad = n_tiles * TN;
+        for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+            s_bias[i] = (p.bias && i < p.n_rows) ? __ldg(p.bias + (i % p.bias_mod)) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -241,7 +249,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
@@ -282,18 +290,36 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         dst_pix = (img * (2 * p.valid_h) + 2 * ih + a) * (long long)(2 * p.valid_w) + 2 * iw + b;
                     }
                     float v[32];
+                    const float* sb = s_bias + n_first;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(r[j]);
-                        if (p.bias) x += __ldg(p.bias + (n_first + j) % p.bias_mod);
-                        if (p.res && n_first + j < p.n_rows) x += p.res[m * (long long)p.n_rows + n_first + j];
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        v[j] = x;
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
+                    if (p.res) {
+                        const float* rp = p.res + m * (long long)p.n_rows + n_first;
+                        if (n_first + 32 <= p.n_rows && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 t = *reinterpret_cast<const float4*>(rp + 4 * q);
+                                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (n_first + j < p.n_rows) v[j] += rp[j];
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
                     const int ncols = min(32, p.n_rows - n_first);
                     if (p.out_f32) {
                         float* o = p.out_f32 + dst_pix * p.out_ld + p.out_c0 + ch0;
-                        for (int j = 0; j < ncols; ++j) o[j] = v[j];
+                        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        } else {
+                            for (int j = 0; j < ncols; ++j) o[j] = v[j];
+                        }
                     } else {
                         __nv_bfloat16* o = p.out + dst_pix * p.out_ld + p.out_c0 + ch0;
                         if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -319,7 +345,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -399,7 +425,7 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     EVFLY_REQUIRE(args, "tc_conv_bf16: null args");
     const evfly_tc_conv_args a = *args;
     EVFLY_REQUIRE(a.x && a.w && (a.out || a.out_f32), "tc_conv_bf16: null tensor");
-    EVFLY_REQUIRE(a.M_rows > 0 && a.M_rows < (1ll << 31) && a.Cin > 0 && a.n_rows > 0, "tc_conv_bf16: bad shape");
+    EVFLY_REQUIRE(a.M_rows > 0 && a.M_rows < (1ll << 31) && a.Cin > 0 && a.n_rows > 0 && a.n_rows <= 2048, "tc_conv_bf16: bad shape (n_rows <= 2048)");
     EVFLY_REQUIRE(a.taps == 1 || a.taps == 9, "tc_conv_bf16: taps must be 1 or 9");
     EVFLY_REQUIRE(a.Cin % 32 == 0, "tc_conv_bf16: Cin must be a multiple of 32 (got %d)", a.Cin);
     EVFLY_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0, "tc_conv_bf16: operands must be 16-byte aligned");

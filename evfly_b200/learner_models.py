@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 from torch.nn import LSTM
 
-from . import ops, vitfly_models
+from . import ops, tc, vitfly_models
 from ._modbase import PackedModule, bn_affine, pack_lstm, run_lstm, to_dev
 from .ConvLSTM_pytorch.convlstm import ConvLSTM
 from .vitfly_models import conv_transpose, pack_conv_transpose
@@ -268,10 +268,27 @@ class OrigUNet(PackedModule):
             mylogger(f'[OrigUNet] FCNet for velocity prediction has {sum(p.numel() for p in self.velpred_head.fcnet.parameters() if p.requires_grad):,} parameters.')
 
     # ---- weights ----------------------------------------------------------------------------
+    precision = 'fp32'     # 'fp32': exact CUDA-core path (rtol 1e-5); 'bf16': tcgen05 tensor-core path (rtol 1e-2)
+
     def _pack(self):
         pk = {f"up{i}": pack_conv_transpose(getattr(self, f"unet_upconv{i}")) for i in range(1, 5)}
         if self.velpred > 0 and self.num_recurrent[1] > 0:
             pk["lstm_velpred"] = pack_lstm(self.lstm_velpred)
+        # bf16 operands of the tensor-core path: [Cout][tap][Cin] for the 3x3 convs,
+        # [phase][Cout][Cin] for the transposed convs, x/h halves of the ConvLSTM gate conv
+        bf = {}
+        for name in ("e12", "e21", "e22", "e31", "e32", "e41", "e42", "e51", "e52",
+                     "d11", "d12", "d21", "d22", "d31", "d32", "d41", "d42"):
+            bf[name] = tc.pack_conv3x3_weight(getattr(self, "unet_" + name).weight)
+        for i in range(1, 5):
+            bf[f"up{i}"] = tc.pack_convt2x2_weight(getattr(self, f"unet_upconv{i}").weight)
+        bf["out"] = tc.pack_conv1x1_weight(self.unet_out.weight)
+        if self.num_recurrent[0] > 0:
+            bf["lstm"] = []
+            for cell in self.lstm.cell_list:
+                w = cell.conv.weight
+                bf["lstm"].append((tc.pack_conv1x1_weight(w[:, :cell.input_dim]), tc.pack_conv1x1_weight(w[:, cell.input_dim:])))
+        pk["bf16"] = bf
         return pk
 
     # ---- pieces of the reference API ------------------------------------------------------------
@@ -298,19 +315,9 @@ class OrigUNet(PackedModule):
         m = getattr(self, name)
         return ops.conv2d(x, m.weight, m.bias, act=act, **kw)
 
-    def forward(self, x):
-        """x = [frames [N,1,H,W], desvel (unused), [h_unet, h_velpred] or None]
-        -> (vel [N,3], (y_interp, y_upconv, (h_unet, h_velpred)))   (learner_models.py:521-616)"""
-        self._check_inference()
-        dev = self._device()
-        pk = self.packed()
-        im = x[0] = to_dev(x[0], dev)
-        N = im.shape[0]
-        if self.num_in_channels == 2 or self.form_BEV > 0:
-            im = self.form_input(im)
-        if x[2] is None:
-            x[2] = (None, None)
-
+    # ---- exact path: CUDA-core fp32 kernels --------------------------------------------------------
+    def _unet_fp32(self, im, state, pk):
+        N, dev = im.shape[0], im.device
         # encoder: (3x3 valid conv + ReLU) x 2 per level, 2x2 max-pool between levels
         y_e1 = self._c("unet_e12", self._c("unet_e11", im))
         y_e2 = self._c("unet_e22", self._c("unet_e21", ops.pool2d(y_e1, 2, 2)))
@@ -320,7 +327,7 @@ class OrigUNet(PackedModule):
 
         h_unet = None
         if self.num_recurrent[0] > 0:
-            y_e5_lstm, h_unet = self.lstm(y_e5.unsqueeze(0), x[2][0])
+            y_e5_lstm, h_unet = self.lstm(y_e5.unsqueeze(0), state)
             y_e5 = y_e5_lstm[0].squeeze(0)
 
         y_upconv = None
@@ -342,11 +349,110 @@ class OrigUNet(PackedModule):
                 y = self._c(f"unet_d{lvl}2", self._c(f"unet_d{lvl}1", cat))
             y_upconv = self._c("unet_out", y, act=None)
             y_interp, y_upconv = self.form_output(y_upconv)
+        return (lambda: y_e5), h_unet, y_upconv, y_interp
+
+    # ---- fast path: bf16 NHWC pitch grids on the tensor cores -----------------------------------
+    def _unet_bf16(self, im, state, W):
+        N, dev = im.shape[0], im.device
+        b = lambda name: getattr(self, "unet_" + name).bias
+        cv = lambda g, name: tc.conv3x3(g, W[name], b(name), relu=True)
+        y_e1 = cv(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12")
+        y_e2 = cv(cv(tc.maxpool2x2(y_e1), "e21"), "e22")
+        y_e3 = cv(cv(tc.maxpool2x2(y_e2), "e31"), "e32")
+        y_e4 = cv(cv(tc.maxpool2x2(y_e3), "e41"), "e42")
+        y_e5 = cv(cv(tc.maxpool2x2(y_e4), "e51"), "e52")
+
+        h_unet = None
+        if self.num_recurrent[0] > 0:
+            y_e5, h_unet = self._convlstm_bf16(y_e5, state, W["lstm"])
+
+        y_upconv = None
+        y_interp = None
+        if not self.is_deployment or (self.is_deployment and (self.velpred == 1 or self.velpred == 11)):
+            y = y_e5
+            for lvl, enc in enumerate((y_e4, y_e3, y_e2, y_e1), start=1):
+                up = getattr(self, f"unet_upconv{lvl}")
+                C = up.out_channels
+                big, small = _SKIP_SIZES[lvl - 1]
+                oh, ow = 2 * y.vh, 2 * y.vw
+                if self.skip_type == 'none':
+                    cat = torch.empty((N, oh, ow, C), dtype=tc.BF16, device=dev)
+                    tc.conv_transpose2x2(y, W[f"up{lvl}"], up.bias, cat, 0)
+                else:
+                    cat = torch.empty((N, oh, ow, 2 * C), dtype=tc.BF16, device=dev)
+                    if self.skip_type == 'crop':
+                        tc.crop_into(enc, big[0] // 2 - small[0] // 2, big[1] // 2 - small[1] // 2, oh, ow, cat, 0)
+                    elif self.skip_type == 'interp':
+                        tc.resize_bilinear_into(enc, oh, ow, cat, 0)
+                    else:
+                        raise ValueError(f'[LEARNER_MODELS/ORIGUNET] skip_type should be crop/interp/none, but is {self.skip_type}.')
+                    tc.conv_transpose2x2(y, W[f"up{lvl}"], up.bias, cat, C)
+                y = cv(cv(tc.Grid(cat, oh, ow), f"d{lvl}1"), f"d{lvl}2")
+            if self.num_out_channels != 1:
+                raise NotImplementedError("num_out_channels == 2 is not used by any shipped configuration")
+            out32 = torch.empty((y.rows, 1), dtype=torch.float32, device=dev)
+            tc.gemm(y.data.view(y.rows, y.C), W["out"], self.unet_out.bias, out_f32=out32)
+            y_upconv = tc.grid_to_nchw(out32.view(N, y.Hp, y.Wp, 1), y.vh, y.vw)
+            y_interp = ops.resize_bilinear(y_upconv, (self.input_h, self.input_w), align_corners=False)
+        return (lambda: tc.grid_to_nchw(y_e5.data, y_e5.vh, y_e5.vw)), h_unet, y_upconv, y_interp
+
+    def _convlstm_bf16(self, g, state, Wl):
+        """ConvLSTM (1x1 kernel, no bias) over the N = time axis on the pitch grid: the x half of the
+        gate conv is ONE tensor-core GEMM over all steps, the h half one small GEMM per step whose
+        epilogue adds the x gates; the cell update is a pointwise kernel (fp32 c, bf16 h)."""
+        T, Hp, Wp, dev = g.N, g.Hp, g.Wp, g.data.device
+        P = Hp * Wp
+        states = []
+        cur = g
+        for li, (wx, wh) in enumerate(Wl):
+            Ch = wh.shape[1]
+            gx = torch.empty((T * P, 4 * Ch), dtype=torch.float32, device=dev)
+            tc.gemm(cur.data.view(T * P, cur.C), wx, None, out_f32=gx)
+            c = torch.zeros((P, Ch), dtype=torch.float32, device=dev)
+            h0 = torch.zeros((P, Ch), dtype=tc.BF16, device=dev)
+            if state is not None:
+                hs, cs = to_dev(state[li][0], dev), to_dev(state[li][1], dev)        # [1,Ch,vh,vw] each
+                h0 = tc.nchw_to_grid(hs, Hp, Wp).data.view(P, Ch)
+                ops.map4d(cs[0].permute(1, 2, 0), c.view(Hp, Wp, Ch)[:g.vh, :g.vw])
+            out = tc.new_grid(T, Hp, Wp, Ch, g.vh, g.vw, dev)
+            hview = out.data.view(T, P, Ch)
+            gxv = gx.view(T, P, 4 * Ch)
+            h_prev = h0
+            for t in range(T):
+                tc.gemm(h_prev, wh, None, out_f32=gxv[t], res_f32=gxv[t])
+                tc.convlstm_pointwise(gxv[t], c, hview[t])
+                h_prev = hview[t]
+            h_last = tc.grid_to_nchw(hview[T - 1].view(1, Hp, Wp, Ch), g.vh, g.vw)
+            c_last = torch.empty((1, Ch, g.vh, g.vw), dtype=torch.float32, device=dev)
+            ops.map4d(c.view(Hp, Wp, Ch)[:g.vh, :g.vw].permute(2, 0, 1), c_last[0])
+            states.append([h_last, c_last])
+            cur = out
+        return cur, states[-1:]
+
+    def forward(self, x):
+        """x = [frames [N,1,H,W], desvel (unused), [h_unet, h_velpred] or None]
+        -> (vel [N,3], (y_interp, y_upconv, (h_unet, h_velpred)))   (learner_models.py:521-616)"""
+        self._check_inference()
+        dev = self._device()
+        pk = self.packed()
+        im = x[0] = to_dev(x[0], dev)
+        N = im.shape[0]
+        if self.num_in_channels == 2 or self.form_BEV > 0:
+            im = self.form_input(im)
+        if x[2] is None:
+            x[2] = (None, None)
+
+        if self.precision == 'bf16':
+            y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_bf16(im, x[2][0], pk["bf16"])
+        else:
+            y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_fp32(im, x[2][0], pk)
 
         y_vel = torch.tensor([1., 0., 0.], device=dev).repeat(N, 1)   # default: forward, full speed
         h_velpred = None
         if self.velpred > 0:
-            src = {1: y_interp, 11: y_upconv, 2: y_e5}[self.velpred]
+            src = {1: y_interp, 11: y_upconv, 2: y_e5_nchw}[self.velpred]
+            if callable(src):
+                src = src()
             feat = self.convnet_velpred(src)
             feat = feat.reshape(N, -1)
             if self.num_recurrent[1] > 0:

@@ -34,6 +34,8 @@ def main():
     m = build_deployed_model("cpu")
     m.load_state_dict(synth_state_dict(shapes_of(m), 31))
     m = m.cuda()
+    import evfly_b200
+    evfly_b200.set_precision(m, os.environ.get("EVFLY_PRECISION", "fp32"))
     pipe = PerceptionPipeline(m, sensor_hw=(260, 346))
     rec, edges = synthetic_stream(0, T, 100_000, 260, 346)
     d, de = to_device(rec), torch.from_numpy(edges).cuda()
