@@ -139,6 +139,16 @@ class AccumulateWorkload:
                 "peak": peaks["hbm_gbs"], "peak_source": peaks["source"] + " (burst copy)", "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": self.alg_bytes}
 
+    @classmethod
+    def cpu_only(cls, rank):
+        from evfly_b200.synthetic import synthetic_window
+        self = cls.__new__(cls)
+        self.host = [synthetic_window(1000 * rank + s, cls.N_EV, cls.H, cls.W) for s in (0, 1)]
+        return self
+
+    def extra(self):
+        return {}
+
     # CPU port of the reference algorithm (oracle): one full window, single thread
     def cpu_step(self, i: int):
         from oracle import ev_oracle as O
@@ -147,13 +157,177 @@ class AccumulateWorkload:
     cpu_cores = 1
 
 
-WORKLOADS = {"accumulate": AccumulateWorkload}
-try:
-    from evfly_b200.bench_pipeline import PipelineWorkload  # added once the forward is on the path
-    WORKLOADS["pipeline"] = PipelineWorkload
-    DEFAULT_WORKLOAD = "pipeline"
-except ImportError:
-    DEFAULT_WORKLOAD = "accumulate"
+class PipelineWorkload:
+    """voxelize + forward (BASELINE metric): per GPU and per step ONE trajectory of 256 consecutive
+    33 ms event windows (cfg-1-style: 260x346, 100k events each = 25.6 M events, 410 MB of records)
+    -> int32 count frames + 5-bin voxel grids (accumulate_windows) -> decode -> 97th-percentile
+    scale/clip -> OrigUNet_w_VITFLY_ViTLSTM (deployed config, bf16 tensor-core path) over the
+    256-step sequence with fresh recurrent state. Configs 3/4 of BASELINE.json: the 256 frames are
+    one sequence; ranks process independent trajectories (weak scaling)."""
+    name = ("cfg3/4: per GPU 1 trajectory x 256 windows (260x346, 100k events each): count frames + 5-bin voxel "
+            "-> prep -> UNet+ConvLSTM+ViT-LSTM forward, bf16 tensor-core path")
+    H, W, B, T, N_EV = 260, 346, 5, 256, 100_000
+    windows_per_step = 256
+    dtype = "bf16"
+    # SURVEY.md 8(d): 2*MAC per frame measured from the reference modules
+    FLOP_UNET, FLOP_CONVLSTM, FLOP_VIT = 11.883e9, 0.436e9, 0.1106e9
+    FLOP_STEM, FLOP_OUT = 0.05e9, 0.0026e9
+
+    def __init__(self, rank: int, device, precision="bf16"):
+        import torch
+        import evfly_b200
+        from evfly_b200.pipeline import PerceptionPipeline, build_deployed_model
+        from evfly_b200.synthetic import synthetic_stream
+        from oracle.synth_ckpt import shapes_of, synth_state_dict
+        self.torch, self.dev = torch, device
+        model = build_deployed_model("cpu")
+        self.sd = synth_state_dict(shapes_of(model), 31)
+        model.load_state_dict(self.sd)
+        self.model = evfly_b200.set_precision(model.to(device).eval(), precision)
+        self.pipe = PerceptionPipeline(self.model, sensor_hw=(self.H, self.W), model_hw=(self.H, self.W), num_bins=self.B)
+        self.host, edges = synthetic_stream(7000 + rank, self.T, self.N_EV, self.H, self.W)
+        self.edges_host = edges
+        self.pinned = torch.from_numpy(self.host.view(np.uint8).reshape(-1, 16)).pin_memory()
+        self.d_in = self.pinned.to(device)
+        self.d_stage = torch.empty_like(self.d_in)
+        self.d_edges = torch.from_numpy(edges).to(device)
+        self.h_vel = torch.empty((self.T, 3), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.pinned.numel()
+        self.d2h_bytes = self.h_vel.numel() * 4
+        self.tc_flops = self.T * (self.FLOP_UNET - self.FLOP_STEM + self.FLOP_CONVLSTM)     # work of k_tc_conv_bf16
+        self.acc_bytes = 16 * self.T * self.N_EV + self.T * self.H * self.W * 4 * (2 + self.B)
+
+    def step(self, i: int):
+        with self.torch.no_grad():
+            self.pipe.reset()
+            self.out = self.pipe(self.d_in, self.d_edges)
+
+    def e2e_step(self, i: int):
+        with self.torch.no_grad():
+            self.d_stage.copy_(self.pinned, non_blocking=True)
+            self.pipe.reset()
+            vel, _, _, _ = self.pipe(self.d_stage, self.d_edges)
+            self.h_vel.copy_(vel, non_blocking=True)
+
+    def dominant(self, i: int):
+        """Same step with CUDA events around every launch of the dominant kernel (k_tc_conv_bf16)
+        and around the accumulation call; sums are read after the timed region."""
+        from evfly_b200 import tc
+        torch = self.torch
+        self._ev = getattr(self, "_ev", [])
+        orig = tc._call
+
+        def timed_call(a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); orig(a); e1.record()
+            self._ev.append((e0, e1))
+        tc._call = timed_call
+        try:
+            with torch.no_grad():
+                self.pipe.reset()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                frames, counts, voxel = self.pipe.frames_from_windows(self.d_in, self.d_edges)
+                a1.record()
+                self._acc_ev = getattr(self, "_acc_ev", []) + [(a0, a1)]
+                self.pipe.forward(frames)
+        finally:
+            tc._call = orig
+
+    def check(self):
+        """one short sequence against the oracle (bf16 tolerance, tests/test_models_bf16_gpu.py)"""
+        import torch
+        from oracle import ev_oracle as O, model_oracle as M
+        T = 4
+        n = T * self.N_EV
+        with torch.no_grad():
+            self.pipe.reset()
+            vel, depth, counts, voxel = self.pipe(self.d_in[:n], self.d_edges[:T + 1])
+            c_ref, _ = O.windows(self.host[:n], self.edges_host[:T + 1], self.H, self.W, B=None)
+            assert np.array_equal(counts.cpu().numpy(), c_ref), "count frames differ from the oracle"
+            fr = 0.2 * (c_ref[:, 1].astype(np.float32) - c_ref[:, 0].astype(np.float32))
+            fr, _ = O.quantile_scale_clip(fr[:, None], 0.97, -1.0, 1.0)
+            ovel, (odep, _, _) = M.orig_unet_w_vitlstm(self.sd, torch.from_numpy(fr), torch.full((T, 1), 4.0), None, None, **M.DEPLOYED_UNET_CFG)
+            l2 = float(torch.linalg.norm(depth.cpu() - odep) / torch.linalg.norm(odep))
+            assert l2 < 1e-2, f"depth differs from the oracle: rel L2 {l2}"
+            assert float((vel.cpu() - ovel).abs().max()) < 1e-2 * float(ovel.abs().mean() + ovel.abs().max())
+            self.pipe.reset()
+
+    def roofline(self, dom_s_unused: float, peaks: dict) -> dict:
+        torch = self.torch
+        torch.cuda.synchronize()
+        n_steps = max(1, len(self._acc_ev))
+        tc_ms = sum(a.elapsed_time(b) for a, b in self._ev)
+        launches = len(self._ev) / n_steps
+        ach = self.tc_flops / (tc_ms / n_steps / 1e3) / 1e12
+        acc_ms = sum(a.elapsed_time(b) for a, b in self._acc_ev) / n_steps
+        self._extra = {"rooflines_other": [{
+            "bound": "hbm", "kernel": "accumulate_windows (k_zero_fill + k_scatter_windows) + decode + quantile",
+            "achieved": self.acc_bytes / (acc_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": self.acc_bytes / (acc_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": self.acc_bytes, "ms": acc_ms}],
+            "tc_kernel_ms_per_step": tc_ms / n_steps}
+        return {"bound": "tensor", "kernel": "k_tc_conv_bf16 (tcgen05 implicit-GEMM conv: all UNet 3x3/1x1/transposed convs + ConvLSTM gates)",
+                "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "algorithmic_flops_per_launch": self.tc_flops / launches, "launches_per_step": launches,
+                "avg_launch_us": tc_ms / n_steps / launches * 1e3}
+
+    def extra(self):
+        return getattr(self, "_extra", {})
+
+    def b1_latency(self, n_windows=200):
+        """BASELINE config 5: batch-1 streaming, 33 ms windows of 100k events at 480x640 already resident
+        in device memory -> velocity command on the host; recurrent state carried; wall clock."""
+        import torch
+        from evfly_b200.pipeline import PerceptionPipeline
+        from evfly_b200.synthetic import synthetic_window
+        pipe = PerceptionPipeline(self.model, sensor_hw=(480, 640), model_hw=(260, 346), num_bins=self.B)
+        wins = [torch.from_numpy(synthetic_window(900 + k, self.N_EV, 480, 640).view(np.uint8).reshape(-1, 16)).to(self.dev) for k in range(8)]
+        edges = torch.tensor([0, 33_333_333], dtype=torch.int64, device=self.dev)
+        lat = []
+        with torch.no_grad():
+            for k in range(n_windows + 10):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                vel, _, _, _ = pipe(wins[k % 8], edges)
+                v = vel.cpu()
+                lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.array(lat[10:])
+        return {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "windows": n_windows,
+                "what": "480x640 window of 100k events resident in HBM -> count frame + voxel -> crop/normalise -> forward -> vel on host"}
+
+    # ---- CPU port of the reference algorithm (oracle/) on a bounded sample --------------------------
+    CPU_T = 8
+    cpu_sample = "1 trajectory of 8 windows (of the step's 256): C accumulation loop + numpy quantile + torch-CPU fp32 forward, all host threads"
+
+    @classmethod
+    def cpu_only(cls, rank):
+        import torch
+        from evfly_b200.pipeline import build_deployed_model
+        from evfly_b200.synthetic import synthetic_stream
+        from oracle.synth_ckpt import shapes_of, synth_state_dict
+        self = cls.__new__(cls)
+        self.sd = synth_state_dict(shapes_of(build_deployed_model("cpu")), 31)
+        self.host, self.edges_host = synthetic_stream(7000 + rank, cls.CPU_T, cls.N_EV, cls.H, cls.W)
+        torch.set_num_threads(os.cpu_count())
+        self.cpu_cores = torch.get_num_threads()
+        self.windows_per_step = cls.CPU_T
+        return self
+
+    def cpu_step(self, i: int):
+        import torch
+        from oracle import ev_oracle as O, model_oracle as M
+        T = self.CPU_T
+        n = T * self.N_EV
+        with torch.no_grad():
+            c_ref, _ = O.windows(self.host[:n], self.edges_host[:T + 1], self.H, self.W, B=self.B)
+            fr = 0.2 * (c_ref[:, 1].astype(np.float32) - c_ref[:, 0].astype(np.float32))
+            fr, _ = O.quantile_scale_clip(fr[:, None], 0.97, -1.0, 1.0)
+            M.orig_unet_w_vitlstm(self.sd, torch.from_numpy(fr), torch.full((T, 1), 4.0), None, None, **M.DEPLOYED_UNET_CFG)
+
+
+WORKLOADS = {"accumulate": AccumulateWorkload, "pipeline": PipelineWorkload}
+DEFAULT_WORKLOAD = "pipeline"
 
 
 # =============================================================================================
@@ -162,14 +336,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     wl_cls = WORKLOADS[args.workload]
-    wl = wl_cls.cpu_only(rank) if hasattr(wl_cls, "cpu_only") else None
-    if wl is None:
-        # accumulate workload needs no device objects for its CPU leg
-        class _Shim(wl_cls):
-            def __init__(self):
-                from evfly_b200.synthetic import synthetic_window
-                self.host = [synthetic_window(s, self.N_EV, self.H, self.W) for s in (0, 1)]
-        wl = _Shim()
+    wl = wl_cls.cpu_only(rank)
     for i in range(args.warmup):
         wl.cpu_step(i)
     t0 = time.perf_counter()
@@ -177,7 +344,7 @@ def run_reference(args, rank, world):
         wl.cpu_step(i)
     dt = time.perf_counter() - t0
     val = wl.windows_per_step * args.steps / dt
-    line = {"impl": "reference", "metric": "event_windows_per_sec", "value": val, "unit": "windows/s",
+    line = {"impl": "reference", "metric": "event windows/sec voxelize+forward", "value": val, "unit": "windows/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
             "data": "synthetic", "config": {"workload": wl.name},
@@ -190,7 +357,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
@@ -261,26 +428,29 @@ def main():
         windows = wl.windows_per_step * world
         value = windows * args.steps / total_s
         line = {
-            "metric": "event_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world,
+            "metric": "event windows/sec voxelize+forward", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
             "data": "synthetic",
             "config": {"workload": wl.name, "windows_per_step_per_gpu": wl.windows_per_step,
-                       "l2_policy": "inputs larger than L2 (rotating 2 x 160 MB event buffers)",
+                       "l2_policy": "inputs larger than L2 (>= 160 MB of event records read per step, outputs >> L2)",
                        "sharding": "independent windows per rank, no data-path collective"},
             "roofline": wl.roofline(dom_s / args.steps, peaks),
             "e2e": {"value": windows * e2e_steps / e2e_s, "unit": "windows/s",
                     "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
             "gpu_launches": launches, "clocks": clocks,
         }
-        if hasattr(wl, "extra"):
-            line.update(wl.extra())
+        line.update(wl.extra())
+        if hasattr(wl, "b1_latency") and world == 1:
+            line["b1_latency"] = wl.b1_latency()
         if world == 1 and not args.no_cpu_baseline:
+            cw = type(wl).cpu_only(rank)
+            cw.cpu_step(0)
             t0 = time.perf_counter()
-            wl.cpu_step(0)
+            cw.cpu_step(1)
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": wl.windows_per_step / dt, "unit": "windows/s", "cores": wl.cpu_cores,
-                                    "kind": "port", "sample": wl.cpu_sample}
+            line["cpu_baseline"] = {"value": cw.windows_per_step / dt, "unit": "windows/s", "cores": cw.cpu_cores,
+                                    "kind": "port", "sample": cw.cpu_sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
