@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, tc
 from ._modbase import PackedModule
 
 
@@ -98,10 +98,50 @@ class MixTransformerEncoderLayer(PackedModule):
         self._ffn = nn.ModuleList([MixFFN(out_channels, expansion_factor) for _ in range(n_layers)])
         self._lNorm = nn.ModuleList([nn.LayerNorm(out_channels) for _ in range(n_layers)])
 
+    precision = 'fp32'     # 'bf16': Linear layers on the tensor cores, bf16 NHWC tokens (evfly_b200.set_precision)
+
+    def _pack(self):
+        c = self.patchMerge.cn1
+        pk = {"patch_w": tc.pack_conv_kc(c.weight), "layers": []}
+        for attn, ffn in zip(self._attn, self._ffn):
+            pk["layers"].append({
+                "red_w": tc.pack_conv_kc(attn.cn1.weight),
+                "kv": tc.pack_conv1x1_weight(attn.keyValueExtractor.weight), "q": tc.pack_conv1x1_weight(attn.query.weight),
+                "final": tc.pack_conv1x1_weight(attn.finalLayer.weight),
+                "mlp1": tc.pack_conv1x1_weight(ffn.mlp1.weight), "mlp2": tc.pack_conv1x1_weight(ffn.mlp2.weight)})
+        return pk
+
+    def encode_bf16(self, x, x_is_f32_nchw, B, H, W):
+        """bf16 path of forward(): x is the fp32 NCHW depth image (stage 1) or the previous stage's
+        bf16 tokens seen as NHWC [B,H,W,Cin]. Returns (tokens bf16 [B,N,C], H', W')."""
+        pk = self.packed()
+        pm, c = self.patchMerge, self.patchMerge.cn1
+        C = c.out_channels
+        tok, H2, W2 = tc.patch_embed_ln(x, x_is_f32_nchw, pk["patch_w"], c.bias, pm.layerNorm.weight, pm.layerNorm.bias, B, H, W,
+                                        c.in_channels, C, c.kernel_size[0], c.stride[0], c.padding[0], pm.layerNorm.eps)
+        N = H2 * W2
+        for attn, ffn, ln, w in zip(self._attn, self._ffn, self._lNorm, pk["layers"]):
+            r = attn.cn1.stride[0]
+            # spatial-reduction attention: k=s=r conv + LayerNorm fused, K/V and Q projections, few-key softmax
+            red, h2, w2 = tc.patch_embed_ln(tok, False, w["red_w"], attn.cn1.bias, attn.ln1.weight, attn.ln1.bias, B, H2, W2, C, C, r, r, 0, attn.ln1.eps)
+            kv = tc.gemm_tokens(red.view(-1, C), w["kv"], attn.keyValueExtractor.bias).view(B, h2 * w2, 2 * C)
+            q = tc.gemm_tokens(tok.view(-1, C), w["q"], attn.query.bias).view(B, N, C)
+            att = tc.attention_small_bf16(q, kv, attn.heads)
+            tok = tc.gemm_tokens(att.view(-1, C), w["final"], attn.finalLayer.bias, res_bf16=tok).view(B, N, C)      # x + attn(x)
+            # MixFFN: Linear -> grouped 3x3 + GELU -> Linear, residual in the last epilogue
+            y1 = tc.gemm_tokens(tok.view(-1, C), w["mlp1"], ffn.mlp1.bias)
+            y2 = tc.dwconv3x3_gelu(y1.view(B, H2, W2, -1), ffn.depthwise.weight, ffn.depthwise.bias)
+            tok = tc.gemm_tokens(y2.view(B * N, -1), w["mlp2"], ffn.mlp2.bias, res_bf16=tok).view(B, N, C)          # x + ffn(x)
+            tok = tc.layernorm_bf16(tok, ln.weight, ln.bias, ln.eps)
+        return tok, H2, W2
+
     def forward(self, x):
         """(B,C,H,W) -> (B,C',H',W') (a channel-last view; ViTsubmodules.py:132-148)."""
         self._check_inference()
         B = x.shape[0]
+        if self.precision == 'bf16' and x.shape[1] == 1:
+            tok, H, W = self.encode_bf16(x.contiguous(), True, B, x.shape[2], x.shape[3])
+            return tc.grid_to_nchw(tok.view(B, H, W, -1), H, W)
         tok, H, W = self.patchMerge(x)
         for i in range(len(self._attn)):
             tok = self._attn[i].forward(tok, H, W, residual=tok)

@@ -78,7 +78,8 @@ class TcConvArgs(C.Structure):
     _fields_ = [("x", _vp), ("w", _vp), ("bias", _vp), ("res_f32", _vp), ("out", _vp), ("out_f32", _vp),
                 ("M_rows", _i64), ("out_ld", _i64),
                 ("Cin", _i32), ("n_rows", _i32), ("taps", _i32), ("w_pitch", _i32), ("relu", _i32), ("out_c0", _i32),
-                ("convt", _i32), ("Hp", _i32), ("Wp", _i32), ("valid_h", _i32), ("valid_w", _i32), ("cout_t", _i32)]
+                ("convt", _i32), ("Hp", _i32), ("Wp", _i32), ("valid_h", _i32), ("valid_w", _i32), ("cout_t", _i32),
+                ("res_bf16", _vp), ("out_gelu", _i32), ("reserved", _i32)]
 
 
 SIGNATURES.update({
@@ -90,6 +91,11 @@ SIGNATURES.update({
     "evfly_convlstm_pointwise_nhwc": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "evfly_nchw_f32_to_nhwc_bf16": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_nhwc_to_nchw_f32": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_patch_embed_ln_bf16": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "evfly_layernorm_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "evfly_attention_small_bf16": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_dwconv3x3_gelu_nhwc_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "evfly_lstm_seq_smemw": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
 })
 
 ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "gelu": 3, "tanh": 4, "sigmoid": 5}

@@ -80,11 +80,16 @@ def pack_lstm(lstm: nn.LSTM):
         b = None
         if lstm.bias:
             b = (getattr(lstm, f"bias_ih_l{l}") + getattr(lstm, f"bias_hh_l{l}")).contiguous()
-        layers.append((w_ih, b, w_hh_t))
+        pairs = None
+        H = lstm.hidden_size
+        if H % 2 == 0 and 4 * H <= 1024 and (H // 2) * 4 * H * 4 + 24 * H <= 220 * 1024:
+            from . import tc
+            pairs = tc.pack_lstm_whh_pairs(getattr(lstm, f"weight_hh_l{l}"))
+        layers.append((w_ih, b, w_hh_t, pairs))
     return layers
 
 
-def run_lstm(ops, packed_layers, seq, state, hidden):
+def run_lstm(ops, packed_layers, seq, state, hidden, smem_weights=False):
     """nn.LSTM forward on an unbatched sequence seq [T,in] with state (h0,c0) [L,H] or None.
     Returns (out [T,H], (h [L,H], c [L,H]))."""
     L = len(packed_layers)
@@ -96,10 +101,18 @@ def run_lstm(ops, packed_layers, seq, state, hidden):
         h0, c0 = to_dev(state[0], dev), to_dev(state[1], dev)
     lib = _lib.load()
     inp = seq
-    for l, (w_ih, b, w_hh_t) in enumerate(packed_layers):
+    for l, (w_ih, b, w_hh_t, pairs) in enumerate(packed_layers):
         gx = ops.linear(inp, w_ih, b)
         T = gx.shape[0]
         hs = torch.empty((T, hidden), dtype=torch.float32, device=dev)
+        if smem_weights and pairs is not None:     # bf16 W_hh resident in shared memory (bf16 path)
+            _lib.check(lib.evfly_lstm_seq_smemw(_lib.ptr(gx), pairs.data_ptr(),
+                                                None if h0 is None else h0[l].data_ptr(),
+                                                None if c0 is None else c0[l].data_ptr(),
+                                                _lib.ptr(hs), h_out[l].data_ptr(), c_out[l].data_ptr(), T, hidden,
+                                                _lib.stream_ptr()), "evfly_lstm_seq_smemw")
+            inp = hs
+            continue
         _lib.check(lib.evfly_lstm_seq_f32(_lib.ptr(gx), _lib.ptr(w_hh_t),
                                           None if h0 is None else h0[l].data_ptr(),
                                           None if c0 is None else c0[l].data_ptr(),

@@ -127,6 +127,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 struct TcArgs {
     const float* bias;     // fp32 [bias_len] or nullptr; indexed by (n % bias_mod)
     const float* res;      // fp32 [M_rows, n_rows] or nullptr, added before the activation
+    const __nv_bfloat16* res16;  // bf16 [M_rows, n_rows] or nullptr (token residuals)
     __nv_bfloat16* out;    // bf16 destination
     float* out_f32;        // optional fp32 destination instead (same addressing)
     long long M_rows;      // rows of the source pitch grid
@@ -306,6 +307,25 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 if (n_first + j < p.n_rows) v[j] += rp[j];
                         }
                     }
+                    if (p.res16) {
+                        const __nv_bfloat16* rp = p.res16 + m * (long long)p.n_rows + n_first;
+                        if (n_first + 32 <= p.n_rows && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 t = *reinterpret_cast<const uint4*>(rp + 8 * q);
+                                const __nv_bfloat162* pt = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __bfloat1622float2(pt[e]);
+                                    v[8 * q + 2 * e] += f.x;
+                                    v[8 * q + 2 * e + 1] += f.y;
+                                }
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (n_first + j < p.n_rows) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
                     if (p.relu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -429,12 +449,13 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     EVFLY_REQUIRE(a.taps == 1 || a.taps == 9, "tc_conv_bf16: taps must be 1 or 9");
     EVFLY_REQUIRE(a.Cin % 32 == 0, "tc_conv_bf16: Cin must be a multiple of 32 (got %d)", a.Cin);
     EVFLY_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0, "tc_conv_bf16: operands must be 16-byte aligned");
-    EVFLY_REQUIRE(!(a.convt && a.res_f32), "tc_conv_bf16: res_f32 is not supported with convt");
+    EVFLY_REQUIRE(!(a.convt && (a.res_f32 || a.res_bf16)), "tc_conv_bf16: residuals are not supported with convt");
     EVFLY_REQUIRE(!a.convt || (a.taps == 1 && a.cout_t % 32 == 0 && a.n_rows == 4 * a.cout_t && a.Hp > 0 && a.Wp > 0 && a.valid_h <= a.Hp && a.valid_w <= a.Wp),
                   "tc_conv_bf16: bad transposed-conv arguments");
     TcArgs p;
     p.bias = a.bias;
     p.res = a.res_f32;
+    p.res16 = reinterpret_cast<const __nv_bfloat16*>(a.res_bf16);
     p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
     p.out_f32 = a.out_f32;
     p.M_rows = a.M_rows;
@@ -454,17 +475,22 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     p.cout_t = a.cout_t;
     cudaStream_t st = (cudaStream_t)stream;
     const bool kc64 = (a.Cin % 64 == 0);
-    // N tile: the whole weight matrix when it fits 256 accumulator columns, else 256-wide tiles
+    // N tile: the whole weight matrix when it fits 256 accumulator columns, else 256-wide tiles;
+    // small-M problems (ConvLSTM step, deep UNet levels at small batch) take narrower tiles so that
+    // m_tiles * n_tiles covers the 148 SMs.
     const int n = a.n_rows;
+    const long long m_tiles = ceil_div(a.M_rows, 128);
+    int tn = n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256));
+    while (tn > 32 && m_tiles * ceil_div(n, tn) < kNumSMs) tn >>= 1;
     if (kc64) {
-        if (n <= 32) return launch_tc<32, 64>(a, p, st);
-        if (n <= 64) return launch_tc<64, 64>(a, p, st);
-        if (n <= 128) return launch_tc<128, 64>(a, p, st);
+        if (tn == 32) return launch_tc<32, 64>(a, p, st);
+        if (tn == 64) return launch_tc<64, 64>(a, p, st);
+        if (tn == 128) return launch_tc<128, 64>(a, p, st);
         return launch_tc<256, 64>(a, p, st);
     } else {
-        if (n <= 32) return launch_tc<32, 32>(a, p, st);
-        if (n <= 64) return launch_tc<64, 32>(a, p, st);
-        if (n <= 128) return launch_tc<128, 32>(a, p, st);
+        if (tn == 32) return launch_tc<32, 32>(a, p, st);
+        if (tn == 64) return launch_tc<64, 32>(a, p, st);
+        if (tn == 128) return launch_tc<128, 32>(a, p, st);
         return launch_tc<256, 32>(a, p, st);
     }
 }

@@ -1,0 +1,317 @@
+// vit_bf16.cu -- bf16 path of the ViT / ViT-LSTM stages (learner/ViTsubmodules.py,
+// learner/vitfly_models.py:132-150). Tokens are bf16 [B, N, C] = NHWC on the stage's H' x W' grid.
+// The Linear layers (query, keyValueExtractor, finalLayer, mlp1, mlp2) run on evfly_tc_conv_bf16;
+// this file holds what is not a GEMM: the (overlap-)patch-embedding convolution fused with its
+// LayerNorm, LayerNorm, the few-key attention, the grouped 3x3 conv + GELU of MixFFN, and the LSTM
+// scan with W_hh resident in shared memory.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace evfly {
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ---------------------------------------------------------------------------------------
+// conv (k x k, stride s, pad p) + bias + LayerNorm(Cout) -> bf16 tokens [B, OH*OW, Cout]
+// one warp per output token; lane l owns channels l, l+32 (Cout <= 64). Input either fp32 NCHW
+// with Cin == 1 (the depth image) or bf16 NHWC. Weights fp32 [K][Cout], K = (kh*k + kw)*Cin + ci.
+// ---------------------------------------------------------------------------------------
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+k_patch_embed_ln(const void* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ bias,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                 int B, int H, int W, int Cin, int Cout, int k, int s, int p, int OH, int OW, float eps) {
+    const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long total = (long long)B * OH * OW;
+    if (tok >= total) return;
+    const int lane = threadIdx.x & 31;
+    const int ow = (int)(tok % OW), oh = (int)((tok / OW) % OH);
+    const long long b = tok / ((long long)OW * OH);
+    const bool two = Cout > 32;
+    float a0 = bias[lane], a1 = two ? bias[lane + 32] : 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+        const int ih = oh * s - p + kh;
+        if ((unsigned)ih >= (unsigned)H) continue;
+        for (int kw = 0; kw < k; ++kw) {
+            const int iw = ow * s - p + kw;
+            if ((unsigned)iw >= (unsigned)W) continue;
+            const float* wp = w + (long long)((kh * k + kw) * Cin) * Cout;
+            if (IN_F32) {
+                const float v = __ldg(reinterpret_cast<const float*>(xin) + (b * H + ih) * (long long)W + iw);
+                a0 = fmaf(v, wp[lane], a0);
+                if (two) a1 = fmaf(v, wp[lane + 32], a1);
+            } else {
+                const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(xin) + ((b * H + ih) * (long long)W + iw) * Cin;
+                for (int c0 = 0; c0 < Cin; c0 += 32) {
+                    const float mine = bf2f(xp[c0 + lane]);  // coalesced 64-byte read, then broadcast by shuffle
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __shfl_sync(0xffffffffu, mine, j);
+                        a0 = fmaf(v, wp[(long long)(c0 + j) * Cout + lane], a0);
+                        if (two) a1 = fmaf(v, wp[(long long)(c0 + j) * Cout + lane + 32], a1);
+                    }
+                }
+            }
+        }
+    }
+    // LayerNorm over Cout
+    float sum = a0 + a1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float mean = sum / (float)Cout;
+    const float d0 = a0 - mean, d1 = two ? a1 - mean : 0.f;
+    float var = d0 * d0 + d1 * d1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+    const float rstd = rsqrtf(var / (float)Cout + eps);
+    __nv_bfloat16* o = out + tok * Cout;
+    o[lane] = __float2bfloat16_rn(d0 * rstd * gamma[lane] + beta[lane]);
+    if (two) o[lane + 32] = __float2bfloat16_rn(d1 * rstd * gamma[lane + 32] + beta[lane + 32]);
+}
+
+// LayerNorm over C (32 or 64) of bf16 rows, one warp per row
+__global__ void __launch_bounds__(256)
+k_layernorm_bf16(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, long long rows, int C, float eps) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const bool two = C > 32;
+    const float a0 = bf2f(x[row * C + lane]), a1 = two ? bf2f(x[row * C + lane + 32]) : 0.f;
+    float sum = a0 + a1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float mean = sum / (float)C;
+    const float d0 = a0 - mean, d1 = two ? a1 - mean : 0.f;
+    float var = d0 * d0 + d1 * d1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+    const float rstd = rsqrtf(var / (float)C + eps);
+    y[row * C + lane] = __float2bfloat16_rn(d0 * rstd * gamma[lane] + beta[lane]);
+    if (two) y[row * C + lane + 32] = __float2bfloat16_rn(d1 * rstd * gamma[lane + 32] + beta[lane + 32]);
+}
+
+// softmax(q k^T / sqrt(d)) v with n_kv <= 8 keys; one thread per (token, head); d = C/heads = 32
+__global__ void __launch_bounds__(128)
+k_attention_small_bf16(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv, __nv_bfloat16* __restrict__ out,
+                       long long B, int N, int C, int heads, int n_kv) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N * heads) return;
+    const int h = (int)(i % heads);
+    const long long bn = i / heads, b = bn / N;
+    const int d = C / heads;
+    const __nv_bfloat16* qp = q + bn * C + h * d;
+    const __nv_bfloat16* kvb = kv + b * n_kv * 2 * C;
+    float qv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) qv[j] = j < d ? bf2f(qp[j]) : 0.f;
+    const float inv = rsqrtf((float)d);
+    float sc[8];
+    float mx = -INFINITY;
+    for (int s = 0; s < n_kv; ++s) {
+        const __nv_bfloat16* kp = kvb + (long long)s * 2 * C + h * d;
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < d) dot = fmaf(qv[j], bf2f(kp[j]), dot);
+        sc[s] = dot * inv;
+        mx = fmaxf(mx, sc[s]);
+    }
+    float den = 0.f;
+    for (int s = 0; s < n_kv; ++s) {
+        sc[s] = __expf(sc[s] - mx);
+        den += sc[s];
+    }
+    const float rden = 1.f / den;
+    __nv_bfloat16* op = out + bn * C + h * d;
+    for (int j = 0; j < d; ++j) {
+        float acc = 0.f;
+        for (int s = 0; s < n_kv; ++s) acc = fmaf(sc[s] * rden, bf2f(kvb[(long long)s * 2 * C + C + h * d + j]), acc);
+        op[j] = __float2bfloat16_rn(acc);
+    }
+}
+
+// MixFFN "depthwise" conv: groups = C, 8 -> 8 channels per group, 3x3, pad 1, + bias + exact GELU.
+// x, y bf16 NHWC [B,H,W,8C]. grid.y = group; each thread one pixel of the group: 8 inputs per tap
+// (one 16-byte load), 576 FMAs against the group's weights in shared memory ([tap][ci][co] fp32).
+__global__ void __launch_bounds__(128)
+k_dwconv3x3_gelu(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 __nv_bfloat16* __restrict__ y, long long B, int H, int W, int Ce) {
+    __shared__ __align__(16) float s_w[9 * 8 * 8];
+    __shared__ float s_b[8];
+    const int g = blockIdx.y;
+    // w is PyTorch's [Ce, 8, 3, 3]: row (g*8 + co), then ci, then tap
+    for (int i = threadIdx.x; i < 576; i += blockDim.x) {
+        const int co = i & 7, ci = (i >> 3) & 7, tap = i >> 6;
+        s_w[i] = w[((long long)(g * 8 + co) * 8 + ci) * 9 + tap];
+    }
+    if (threadIdx.x < 8) s_b[threadIdx.x] = bias[g * 8 + threadIdx.x];
+    __syncthreads();
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= B * H * W) return;
+    const int pw = (int)(pix % W), ph = (int)((pix / W) % H);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = s_b[c];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ih = ph + tap / 3 - 1, iw = pw + tap % 3 - 1;
+        if ((unsigned)ih >= (unsigned)H || (unsigned)iw >= (unsigned)W) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + (pix + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * Ce + g * 8);
+        const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float in[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(pr[q]);
+            in[2 * q] = f.x;
+            in[2 * q + 1] = f.y;
+        }
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[(tap * 8 + ci) * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[(tap * 8 + ci) * 8 + 4]);
+            acc[0] = fmaf(in[ci], w0.x, acc[0]); acc[1] = fmaf(in[ci], w0.y, acc[1]);
+            acc[2] = fmaf(in[ci], w0.z, acc[2]); acc[3] = fmaf(in[ci], w0.w, acc[3]);
+            acc[4] = fmaf(in[ci], w1.x, acc[4]); acc[5] = fmaf(in[ci], w1.y, acc[5]);
+            acc[6] = fmaf(in[ci], w1.z, acc[6]); acc[7] = fmaf(in[ci], w1.w, acc[7]);
+        }
+    }
+    uint4 o;
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float a = acc[2 * q], b2 = acc[2 * q + 1];
+        const float ga = 0.5f * a * (1.f + erff(a * 0.70710678118654752440f));
+        const float gb = 0.5f * b2 * (1.f + erff(b2 * 0.70710678118654752440f));
+        po[q] = __floats2bfloat162_rn(ga, gb);
+    }
+    *reinterpret_cast<uint4*>(y + pix * Ce + g * 8) = o;
+}
+
+// ---------------------------------------------------------------------------------------
+// LSTM layer over an unbatched sequence with W_hh^T resident in shared memory as bf16 pairs:
+// s_w[(j/2) * 4H + r] = {W_hh[r][j], W_hh[r][j+1]}. One persistent CTA of 4H threads; thread r owns
+// gate row r. h and c stay fp32 in shared memory across all T steps.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_lstm_seq_smemw(const float* __restrict__ gx, const __nv_bfloat162* __restrict__ whh_pairs, const float* __restrict__ h0,
+                 const float* __restrict__ c0, float* __restrict__ hs, float* __restrict__ hT, float* __restrict__ cT, int T,
+                 int H) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int G = 4 * H;
+    __nv_bfloat162* s_w = reinterpret_cast<__nv_bfloat162*>(sm_raw);        // [H/2][G]
+    float* s_h = reinterpret_cast<float*>(sm_raw + (size_t)(H / 2) * G * 4);  // [H]
+    float* s_c = s_h + H;                                                     // [H]
+    float* s_g = s_c + H;                                                     // [G]
+    for (int i = threadIdx.x; i < (H / 2) * G; i += blockDim.x) s_w[i] = whh_pairs[i];
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        s_h[j] = h0 ? h0[j] : 0.f;
+        s_c[j] = c0 ? c0[j] : 0.f;
+    }
+    __syncthreads();
+    const int r = threadIdx.x;
+    for (int t = 0; t < T; ++t) {
+        if (r < G) {
+            float acc0 = gx[(long long)t * G + r], acc1 = 0.f;
+#pragma unroll 8
+            for (int j2 = 0; j2 < H / 2; ++j2) {
+                const float2 wv = __bfloat1622float2(s_w[j2 * G + r]);
+                const float2 hv = *reinterpret_cast<const float2*>(&s_h[2 * j2]);
+                acc0 = fmaf(hv.x, wv.x, acc0);
+                acc1 = fmaf(hv.y, wv.y, acc1);
+            }
+            s_g[r] = acc0 + acc1;
+        }
+        __syncthreads();
+        if (r < H) {
+            const float ig = 1.f / (1.f + __expf(-s_g[r]));
+            const float fg = 1.f / (1.f + __expf(-s_g[H + r]));
+            const float gg = tanhf(s_g[2 * H + r]);
+            const float og = 1.f / (1.f + __expf(-s_g[3 * H + r]));
+            const float c = fg * s_c[r] + ig * gg;
+            const float h = og * tanhf(c);
+            s_c[r] = c;
+            s_h[r] = h;
+            hs[(long long)t * H + r] = h;
+        }
+        __syncthreads();
+    }
+    if (r < H) {
+        if (hT) hT[r] = s_h[r];
+        if (cT) cT[r] = s_c[r];
+    }
+}
+
+}  // namespace evfly
+
+using namespace evfly;
+
+extern "C" int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, const float* d_w_kc, const float* d_bias,
+                                         const float* d_gamma, const float* d_beta, void* d_tokens, int B, int H, int W, int Cin,
+                                         int Cout, int k, int stride, int pad, float eps, void* stream) {
+    EVFLY_REQUIRE(d_x && d_w_kc && d_bias && d_gamma && d_beta && d_tokens, "patch_embed_ln_bf16: null pointer");
+    EVFLY_REQUIRE(B >= 0 && H > 0 && W > 0 && k > 0 && stride > 0 && pad >= 0 && (Cout == 32 || Cout == 64), "patch_embed_ln_bf16: bad shape (Cout must be 32 or 64)");
+    EVFLY_REQUIRE(x_is_f32_nchw ? Cin == 1 : (Cin % 32 == 0), "patch_embed_ln_bf16: fp32 input needs Cin == 1, bf16 NHWC input Cin %% 32 == 0");
+    if (B == 0) return EVFLY_OK;
+    const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+    EVFLY_REQUIRE(OH > 0 && OW > 0, "patch_embed_ln_bf16: empty output");
+    const long long total = (long long)B * OH * OW;
+    const unsigned grid = (unsigned)ceil_div(total, 8);
+    if (x_is_f32_nchw)
+        k_patch_embed_ln<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), B, H, W, Cin, Cout, k, stride, pad, OH, OW, eps);
+    else
+        k_patch_embed_ln<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), B, H, W, Cin, Cout, k, stride, pad, OH, OW, eps);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_layernorm_bf16(const void* d_x, const float* d_gamma, const float* d_beta, void* d_y, int64_t rows, int C,
+                                    float eps, void* stream) {
+    EVFLY_REQUIRE(d_x && d_gamma && d_beta && d_y && rows >= 0 && (C == 32 || C == 64), "layernorm_bf16: bad argument (C must be 32 or 64)");
+    if (rows == 0) return EVFLY_OK;
+    k_layernorm_bf16<<<(unsigned)ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d_x), d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_y), rows, C, eps);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_attention_small_bf16(const void* d_q, const void* d_kv, void* d_out, int64_t B, int N, int C, int heads,
+                                          int n_kv, void* stream) {
+    EVFLY_REQUIRE(d_q && d_kv && d_out && B >= 0 && N > 0 && heads > 0 && C % heads == 0 && C / heads <= 32 && n_kv > 0 && n_kv <= 8,
+                  "attention_small_bf16: bad argument (head dim <= 32, n_kv <= 8)");
+    if (B == 0) return EVFLY_OK;
+    const long long total = B * N * heads;
+    k_attention_small_bf16<<<(unsigned)ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d_q), reinterpret_cast<const __nv_bfloat16*>(d_kv), reinterpret_cast<__nv_bfloat16*>(d_out), B, N, C, heads, n_kv);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_dwconv3x3_gelu_nhwc_bf16(const void* d_x, const float* d_w, const float* d_bias, void* d_y, int64_t B, int H,
+                                              int W, int Ce, void* stream) {
+    EVFLY_REQUIRE(d_x && d_w && d_bias && d_y && B >= 0 && H > 0 && W > 0 && Ce % 8 == 0, "dwconv3x3_gelu_nhwc_bf16: bad argument");
+    if (B == 0) return EVFLY_OK;
+    const long long pixels = B * H * W;
+    dim3 grid((unsigned)ceil_div(pixels, 128), (unsigned)(Ce / 8));
+    k_dwconv3x3_gelu<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_bias,
+                                                             reinterpret_cast<__nv_bfloat16*>(d_y), B, H, W, Ce);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float* d_h0, const float* d_c0, float* d_hs,
+                                    float* d_hT, float* d_cT, int T, int H, void* stream) {
+    EVFLY_REQUIRE(d_gx && d_whh_pairs && d_hs && T >= 0 && H > 0 && H % 2 == 0 && 4 * H <= 1024, "lstm_seq_smemw: bad argument (H even, 4H <= 1024)");
+    const size_t smem = (size_t)(H / 2) * 4 * H * 4 + (size_t)6 * H * 4;
+    EVFLY_REQUIRE(smem <= 220 * 1024, "lstm_seq_smemw: W_hh does not fit shared memory (H=%d)", H);
+    static bool attr = false;
+    if (!attr) {
+        EVFLY_CUDA(cudaFuncSetAttribute(k_lstm_seq_smemw, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    const int threads = ((4 * H + 31) / 32) * 32;
+    k_lstm_seq_smemw<<<1, threads, smem, (cudaStream_t)stream>>>(d_gx, reinterpret_cast<const __nv_bfloat162*>(d_whh_pairs), d_h0, d_c0,
+                                                                 d_hs, d_hT, d_cT, T, H);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}

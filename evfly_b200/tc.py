@@ -156,3 +156,63 @@ def grid_to_nchw(data, vh, vw) -> torch.Tensor:
     _lib.check(_lib.load().evfly_nhwc_to_nchw_f32(data.data_ptr(), int(data.dtype == torch.float32), _lib.ptr(out), N, Cc, vh, vw,
                                                    Hp, Wp, _lib.stream_ptr()), "evfly_nhwc_to_nchw_f32")
     return out
+
+
+# ---- bf16 ViT stage helpers ------------------------------------------------------------------------
+def gemm_tokens(x2d, w_packed, bias=None, res_bf16=None, relu=False):
+    """bf16 [M,K] @ [N,K]^T + bias (+ bf16 residual) -> bf16 [M,N] on the tensor cores."""
+    M, K = x2d.shape
+    Nn = w_packed.shape[0]
+    assert x2d.is_contiguous() and x2d.dtype == BF16
+    out = torch.empty((M, Nn), dtype=BF16, device=x2d.device)
+    a = _lib.TcConvArgs()
+    a.x, a.w, a.bias, a.out = x2d.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data_ptr()
+    a.res_bf16 = None if res_bf16 is None else res_bf16.data_ptr()
+    a.M_rows, a.out_ld = M, Nn
+    a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = K, Nn, 1, 0, int(relu), 0
+    _call(a)
+    return out
+
+
+def pack_conv_kc(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,k,k] fp32 -> fp32 [k*k*Cin, Cout] with K index (kh*k+kw)*Cin + ci."""
+    return w.permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous()
+
+
+def patch_embed_ln(x, x_is_f32_nchw, w_kc, bias, gamma, beta, B, H, W, Cin, Cout, k, stride, pad, eps):
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    tok = torch.empty((B, OH * OW, Cout), dtype=BF16, device=x.device)
+    _lib.check(_lib.load().evfly_patch_embed_ln_bf16(x.data_ptr(), int(x_is_f32_nchw), _lib.ptr(w_kc), _lib.ptr(bias), _lib.ptr(gamma),
+                                                     _lib.ptr(beta), tok.data_ptr(), B, H, W, Cin, Cout, k, stride, pad, eps,
+                                                     _lib.stream_ptr()), "evfly_patch_embed_ln_bf16")
+    return tok, OH, OW
+
+
+def layernorm_bf16(x, gamma, beta, eps):
+    y = torch.empty_like(x)
+    Cc = x.shape[-1]
+    _lib.check(_lib.load().evfly_layernorm_bf16(x.data_ptr(), _lib.ptr(gamma), _lib.ptr(beta), y.data_ptr(), x.numel() // Cc, Cc, eps,
+                                                _lib.stream_ptr()), "evfly_layernorm_bf16")
+    return y
+
+
+def attention_small_bf16(q, kv, heads):
+    B, N, Cc = q.shape
+    out = torch.empty_like(q)
+    _lib.check(_lib.load().evfly_attention_small_bf16(q.data_ptr(), kv.data_ptr(), out.data_ptr(), B, N, Cc, heads, kv.shape[1],
+                                                      _lib.stream_ptr()), "evfly_attention_small_bf16")
+    return out
+
+
+def dwconv3x3_gelu(x_bhwc, w, bias):
+    B, H, W, Ce = x_bhwc.shape
+    y = torch.empty_like(x_bhwc)
+    _lib.check(_lib.load().evfly_dwconv3x3_gelu_nhwc_bf16(x_bhwc.data_ptr(), _lib.ptr(w), _lib.ptr(bias), y.data_ptr(), B, H, W, Ce,
+                                                          _lib.stream_ptr()), "evfly_dwconv3x3_gelu_nhwc_bf16")
+    return y
+
+
+def pack_lstm_whh_pairs(w_hh: torch.Tensor) -> torch.Tensor:
+    """W_hh [4H,H] -> bf16 [H/2, 4H, 2] = {W[r][2j], W[r][2j+1]} at [j][r]."""
+    G, H = w_hh.shape
+    return w_hh.t().reshape(H // 2, 2, G).permute(0, 2, 1).to(BF16).contiguous()

@@ -10,7 +10,7 @@ import torch.nn as nn
 import torch.nn.utils.spectral_norm as spectral_norm
 from torch.nn import LSTM
 
-from . import ops
+from . import ops, tc
 from ._modbase import PackedModule, bn_affine, pack_lstm, run_lstm, sn_effective_weight, to_dev
 from .ViTsubmodules import *  # noqa: F401,F403  (the reference does the same)
 from .ViTsubmodules import MixTransformerEncoderLayer
@@ -64,11 +64,20 @@ class _ViTEncoder(PackedModule):
         self.pxShuffle = nn.PixelShuffle(upscale_factor=2)
         self.down_sample = nn.Conv2d(48, 12, 3, padding=1)
 
+    precision = 'fp32'
+
     def _encode(self, depth):
         """[N,1,60,90] -> [N,4608] features."""
-        s1 = self.encoder_blocks[0](depth)          # [N,32,15,23] view
-        s2 = self.encoder_blocks[1](s1)             # [N,64,8,12] view
         N = depth.shape[0]
+        if self.precision == 'bf16':
+            b0, b1 = self.encoder_blocks
+            t1, H1, W1 = b0.encode_bf16(depth.contiguous(), True, N, depth.shape[2], depth.shape[3])
+            t2, H2, W2 = b1.encode_bf16(t1, False, N, H1, W1)
+            s1 = tc.grid_to_nchw(t1.view(N, H1, W1, -1), H1, W1)      # [N,32,15,23] fp32 for the small fp32 tail
+            s2 = tc.grid_to_nchw(t2.view(N, H2, W2, -1), H2, W2)      # [N,64,8,12]
+        else:
+            s1 = self.encoder_blocks[0](depth)          # [N,32,15,23] view
+            s2 = self.encoder_blocks[1](s1)             # [N,64,8,12] view
         cat = torch.empty((N, 48, 16, 24), dtype=torch.float32, device=depth.device)
         ops.pixel_shuffle(s2, 2, cat[:, :16])
         ops.resize_bilinear(s1, (16, 24), align_corners=True, out_view=cat[:, 16:])
@@ -101,7 +110,7 @@ class LSTMNetVIT(_ViTEncoder):
         seq, feat_out = _meta_concat(512, [(X[1], 1.0, 10.0), (X[2], 1.0, 1.0)], N, feat.device)   # X[1]/10
         ops.linear(feat, pk["decoder"], self.decoder.bias, out2d=feat_out)
         state = X[3] if len(X) > 3 else None
-        out, h = run_lstm(ops, pk["lstm"], seq, state, 128)
+        out, h = run_lstm(ops, pk["lstm"], seq, state, 128, smem_weights=self.precision == 'bf16')
         out = ops.linear(out, pk["fc2"], self.nn_fc2.bias)
         return out, h
 

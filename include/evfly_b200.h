@@ -313,6 +313,9 @@ typedef struct evfly_tc_conv_args {
     int64_t out_ld;
     int32_t Cin, n_rows, taps, w_pitch, relu, out_c0;
     int32_t convt, Hp, Wp, valid_h, valid_w, cout_t;
+    const void*  res_bf16;   /* optional bf16 [M_rows, n_rows] residual (x + attn(x), x + ffn(x)) */
+    int32_t out_gelu;        /* reserved, must be 0 */
+    int32_t reserved;
 } evfly_tc_conv_args;
 int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream);
 
@@ -349,6 +352,29 @@ int evfly_nchw_f32_to_nhwc_bf16(const float* d_x, void* d_y, int N, int C, int v
                                 void* stream);
 int evfly_nhwc_to_nchw_f32(const void* d_x, int src_is_f32, float* d_y, int N, int C, int vh, int vw, int Hp,
                            int Wp, void* stream);
+
+/* ---- bf16 path of the ViT / ViT-LSTM stages (tokens bf16 [B, N, C] = NHWC on the H' x W' grid) ---- */
+
+/* OverlapPatchMerging / the attention's reduction conv (ViTsubmodules.py:15-34, 43-44, 68-70):
+ * conv(k, stride, pad) + bias + LayerNorm(Cout) fused, one warp per output token.
+ * x: fp32 NCHW with Cin == 1 (x_is_f32_nchw) or bf16 NHWC [B,H,W,Cin]; w_kc fp32 [k*k*Cin][Cout]
+ * with K index (kh*k + kw)*Cin + ci; tokens bf16 [B, OH*OW, Cout]; Cout in {32, 64}.           */
+int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, const float* d_w_kc, const float* d_bias,
+                              const float* d_gamma, const float* d_beta, void* d_tokens, int B, int H, int W,
+                              int Cin, int Cout, int k, int stride, int pad, float eps, void* stream);
+int evfly_layernorm_bf16(const void* d_x, const float* d_gamma, const float* d_beta, void* d_y, int64_t rows,
+                         int C, float eps, void* stream);
+/* q bf16 [B,N,C], kv bf16 [B,n_kv,2C] ([key|value][head][d]) -> out bf16 [B,N,C]; n_kv <= 8.      */
+int evfly_attention_small_bf16(const void* d_q, const void* d_kv, void* d_out, int64_t B, int N, int C,
+                               int heads, int n_kv, void* stream);
+/* MixFFN's grouped conv (groups = C, 8 -> 8 per group, 3x3, 'same') + bias + exact GELU on bf16
+ * NHWC [B,H,W,Ce]; w is PyTorch's fp32 [Ce, 8, 3, 3] (ViTsubmodules.py:92,113).                   */
+int evfly_dwconv3x3_gelu_nhwc_bf16(const void* d_x, const float* d_w, const float* d_bias, void* d_y, int64_t B,
+                                   int H, int W, int Ce, void* stream);
+/* evfly_lstm_seq_f32 with W_hh resident in shared memory as bf16: d_whh_pairs is bf16x2
+ * [H/2][4H] = {W_hh[r][2j], W_hh[r][2j+1]} at [j][r]; state and gates stay fp32. 4H <= 1024.       */
+int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float* d_h0, const float* d_c0,
+                         float* d_hs, float* d_hT, float* d_cT, int T, int H, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,3 +99,22 @@ def test_full_model_bf16_sequence(cuda_lib, manifest):
     vel32, (dep32, _, _) = m([frames.clone().cuda(), dv.cuda(), [None, None], None])
     np.testing.assert_allclose(dep32.cpu().numpy(), odep.numpy(), rtol=1e-5, atol=2e-5)
     close_bf16(dep, dep32.cpu(), "depth bf16 vs fp32 path")
+
+
+def test_lstmnetvit_bf16_vs_oracle(cuda_lib, manifest):
+    from oracle.synth_ckpt import synthetic_depth
+    m = load("LSTMNetVIT", manifest, 11, "bf16")
+    sd = synth_state_dict(manifest["LSTMNetVIT"], 11)
+    depth = synthetic_depth(1, 12)
+    dv = torch.full((12, 1), 4.0)
+    vel, (h, c) = m([depth.clone().cuda(), dv.cuda(), None])
+    ovel, (oh, oc) = M.lstmnet_vit(sd, depth.clone(), dv, None)
+    close_bf16(vel, ovel, "vel", rel_l2=2e-2, max_scale=5e-2)
+    close_bf16(h, oh, "h", rel_l2=3e-2, max_scale=0.2); close_bf16(c, oc, "c", rel_l2=3e-2, max_scale=0.2)
+    # the two encoder stages on their own
+    s1 = M.mix_transformer_stage(sd, "encoder_blocks.0", depth, **M.STAGE1)
+    t1, H1, W1 = m.encoder_blocks[0].encode_bf16(depth.cuda(), True, 12, 60, 90)
+    close_bf16(t1.view(12, H1, W1, 32).permute(0, 3, 1, 2), s1, "stage 1", rel_l2=2e-2, max_scale=0.15)
+    s2 = M.mix_transformer_stage(sd, "encoder_blocks.1", s1, **M.STAGE2)
+    t2, H2, W2 = m.encoder_blocks[1].encode_bf16(t1, False, 12, H1, W1)
+    close_bf16(t2.view(12, H2, W2, 64).permute(0, 3, 1, 2), s2, "stage 2", rel_l2=3e-2, max_scale=0.2)

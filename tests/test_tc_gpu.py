@@ -103,3 +103,74 @@ def test_nhwc_glue(cuda_lib):
     tc.convlstm_pointwise(gates.cuda(), dc, dh)
     np.testing.assert_allclose(dc.cpu().numpy(), cn.numpy(), rtol=1e-5, atol=1e-5)
     check_bf16(dh, hn, "convlstm h")
+
+
+# ---- bf16 ViT kernels ---------------------------------------------------------------------------
+def test_patch_embed_ln_and_reduction_conv(cuda_lib):
+    B = 3
+    # stage 1: fp32 depth image, 7x7 stride 4 pad 3, 1 -> 32, LayerNorm
+    x = rnd(B, 1, 60, 90, seed=1)
+    w, b, g, be = rnd(32, 1, 7, 7, seed=2, scale=0.15), rnd(32, seed=3), 1 + 0.1 * rnd(32, seed=4), 0.1 * rnd(32, seed=5)
+    y = F.conv2d(x, w, b, stride=4, padding=3)
+    want = F.layer_norm(y.flatten(2).transpose(1, 2), (32,), g, be)
+    tok, H, W = tc.patch_embed_ln(x.cuda(), True, tc.pack_conv_kc(w.cuda()), b.cuda(), g.cuda(), be.cuda(), B, 60, 90, 1, 32, 7, 4, 3, 1e-5)
+    assert (H, W) == (15, 23)
+    check_bf16(tok, want, "patch embed 1")
+    # stage 2 and the reduction convs: bf16 NHWC input
+    for Cin, Cout, k, s, p, Hh, Ww in [(32, 64, 3, 2, 1, 15, 23), (32, 32, 8, 8, 0, 15, 23), (64, 64, 4, 4, 0, 8, 12)]:
+        xt = bf(rnd(B, Hh * Ww, Cin, seed=6))
+        w, b = rnd(Cout, Cin, k, k, seed=7, scale=(Cin * k * k) ** -0.5), rnd(Cout, seed=8)
+        g, be = 1 + 0.1 * rnd(Cout, seed=9), 0.1 * rnd(Cout, seed=10)
+        y = F.conv2d(xt.view(B, Hh, Ww, Cin).permute(0, 3, 1, 2), w, b, stride=s, padding=p)
+        want = F.layer_norm(y.flatten(2).transpose(1, 2), (Cout,), g, be)
+        tok, H, W = tc.patch_embed_ln(xt.to(BF).cuda(), False, tc.pack_conv_kc(w.cuda()), b.cuda(), g.cuda(), be.cuda(), B, Hh, Ww, Cin, Cout, k, s, p, 1e-5)
+        assert tok.shape == want.shape
+        check_bf16(tok, want, f"patch embed {Cin}->{Cout} k{k}")
+
+
+def test_layernorm_attention_dwconv_bf16(cuda_lib):
+    for C in (32, 64):
+        x, g, b = bf(rnd(500, C, seed=1) * 2 + 0.5), rnd(C, seed=2), rnd(C, seed=3)
+        check_bf16(tc.layernorm_bf16(x.to(BF).cuda(), g.cuda(), b.cuda(), 1e-5), F.layer_norm(x, (C,), g, b), "layernorm")
+    for B, N, C, heads, nkv in [(3, 345, 32, 1, 2), (3, 96, 64, 2, 6)]:
+        q, kv = bf(rnd(B, N, C, seed=1)), bf(rnd(B, nkv, 2 * C, seed=2))
+        d = C // heads
+        kvr = kv.reshape(B, nkv, 2, heads, d).permute(2, 0, 3, 1, 4)
+        qr = q.reshape(B, N, heads, d).permute(0, 2, 1, 3)
+        att = torch.softmax(qr @ kvr[0].transpose(-2, -1) / d ** 0.5, dim=-1)
+        want = (att @ kvr[1]).transpose(1, 2).reshape(B, N, C)
+        check_bf16(tc.attention_small_bf16(q.to(BF).cuda(), kv.to(BF).cuda(), heads), want, "attention")
+    for B, H, W, C in [(2, 15, 23, 32), (2, 8, 12, 64)]:
+        Ce = 8 * C
+        x = bf(rnd(B, H, W, Ce, seed=1))
+        w, b = rnd(Ce, 8, 3, 3, seed=2, scale=72 ** -0.5), rnd(Ce, seed=3)
+        want = F.gelu(F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1, groups=C)).permute(0, 2, 3, 1)
+        check_bf16(tc.dwconv3x3_gelu(x.to(BF).cuda(), w.cuda(), b.cuda()), want, "dwconv+gelu")
+
+
+def test_gemm_tokens_residual_and_small_m_tiles(cuda_lib):
+    M, K, N = 1035, 256, 32
+    x, w, b, r = bf(rnd(M, K, seed=1)), bf(rnd(N, K, seed=2, scale=K ** -0.5)), rnd(N, seed=3), bf(rnd(M, N, seed=4))
+    got = tc.gemm_tokens(x.to(BF).cuda(), w.to(BF).cuda(), b.cuda(), res_bf16=r.to(BF).cuda())
+    check_bf16(got, x.double() @ w.double().t() + b.double() + r.double(), "gemm + bf16 residual")
+    # small M, wide N: the launcher narrows the N tile to fill the SMs (ConvLSTM step shape)
+    M, K, N = 204, 512, 2048
+    x, w = bf(rnd(M, K, seed=5)), bf(rnd(N, K, seed=6, scale=K ** -0.5))
+    check_bf16(tc.gemm(x.to(BF).cuda(), w.to(BF).cuda()), x.double() @ w.double().t(), "small-M gemm")
+
+
+def test_lstm_smem_weights(cuda_lib):
+    from evfly_b200 import ops
+    from evfly_b200._modbase import pack_lstm, run_lstm
+    torch.manual_seed(0)
+    m = torch.nn.LSTM(input_size=517, hidden_size=128, num_layers=3).eval()
+    x = rnd(40, 517, seed=1)
+    h0, c0 = rnd(3, 128, seed=2) * 0.3, rnd(3, 128, seed=3) * 0.3
+    with torch.no_grad():
+        want, (hn, cn) = m(x, (h0, c0))
+        mc = m.cuda()
+        got, (h, c) = run_lstm(ops, pack_lstm(mc), x.cuda(), (h0, c0), 128, smem_weights=True)
+    # W_hh is rounded to bf16 (2^-9 relative), everything else fp32
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-2, atol=3e-3)
+    np.testing.assert_allclose(h.cpu().numpy(), hn.numpy(), rtol=2e-2, atol=3e-3)
+    np.testing.assert_allclose(c.cpu().numpy(), cn.numpy(), rtol=2e-2, atol=3e-3)
