@@ -59,6 +59,7 @@ class ConvArgs(C.Structure):
 _p64 = C.POINTER(_i64)
 SIGNATURES.update({
     "evfly_conv2d_f32": (_i32, [C.POINTER(ConvArgs), _vp]),
+    "evfly_linear_smallm_f32": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "evfly_pool2d_f32": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_resize_bilinear_f32": (_i32, [_vp, _p64, _vp, _p64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp]),
     "evfly_layernorm_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),

@@ -105,7 +105,7 @@ def run_lstm(ops, packed_layers, seq, state, hidden, smem_weights=False):
         gx = ops.linear(inp, w_ih, b)
         T = gx.shape[0]
         hs = torch.empty((T, hidden), dtype=torch.float32, device=dev)
-        if smem_weights and pairs is not None:     # bf16 W_hh resident in shared memory (bf16 path)
+        if smem_weights and pairs is not None and T >= 16:     # bf16 W_hh resident in shared memory (bf16 path, long sequences)
             _lib.check(lib.evfly_lstm_seq_smemw(_lib.ptr(gx), pairs.data_ptr(),
                                                 None if h0 is None else h0[l].data_ptr(),
                                                 None if c0 is None else c0[l].data_ptr(),

@@ -141,6 +141,46 @@ k_conv2d_f32(const evfly_conv2d_args a, const int OH, const int OW, const long l
 }
 
 // ---------------------------------------------------------------------------------------
+// Linear with a handful of rows (batch-1 streaming: the 4608->512 decoder, the LSTM input
+// projection, the heads): weight-bandwidth bound, so one warp per output feature streams its
+// weight row once (coalesced) and serves all M <= 8 input rows from shared memory.
+// ---------------------------------------------------------------------------------------
+constexpr int kSmallM = 8;
+__global__ void __launch_bounds__(256)
+k_linear_smallm(const float* __restrict__ x, long long x_ld, const float* __restrict__ w, const float* __restrict__ bias,
+                const float* __restrict__ res, long long res_ld, float* __restrict__ y, long long y_ld, int M, int N, int K, int act) {
+    extern __shared__ float s_x[];  // [M][K]
+    for (int i = threadIdx.x; i < M * K; i += blockDim.x) s_x[i] = x[(long long)(i / K) * x_ld + (i % K)];
+    __syncthreads();
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    float acc[kSmallM];
+#pragma unroll
+    for (int m = 0; m < kSmallM; ++m) acc[m] = 0.f;
+    const float* wr = w + (long long)n * K;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(wr + k);
+#pragma unroll
+        for (int m = 0; m < kSmallM; ++m)
+            if (m < M) acc[m] = fmaf(s_x[m * K + k], wv, acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < kSmallM; ++m) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], d);
+    }
+    if (lane == 0) {
+        for (int m = 0; m < M; ++m) {
+            float v = acc[m] + (bias ? bias[n] : 0.f);
+            v = apply_act(v, act);
+            if (res) v += res[(long long)m * res_ld + n];
+            y[(long long)m * y_ld + n] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -436,6 +476,21 @@ extern "C" int evfly_conv2d_f32(const evfly_conv2d_args* p, void* stream) {
     EVFLY_REQUIRE(gx < (1ll << 31) && a.groups < 65536, "conv2d_f32: problem too large for one grid");
     dim3 grid((unsigned)gx, (unsigned)ceil_div(cout_g, CBN), (unsigned)a.groups);
     k_conv2d_f32<<<grid, 256, 0, (cudaStream_t)stream>>>(a, OH, OW, M, K, cin_g, cout_g);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_linear_smallm_f32(const float* d_x, int64_t x_ld, const float* d_w, const float* d_bias, const float* d_res,
+                                       int64_t res_ld, float* d_y, int64_t y_ld, int M, int N, int K, int act, void* stream) {
+    EVFLY_REQUIRE(d_x && d_w && d_y && M > 0 && M <= kSmallM && N > 0 && K > 0 && (size_t)M * K * 4 <= 160 * 1024, "linear_smallm_f32: bad argument (M <= 8)");
+    EVFLY_REQUIRE(act >= 0 && act <= EVFLY_ACT_SIGMOID, "linear_smallm_f32: bad activation");
+    const size_t smem = (size_t)M * K * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        EVFLY_CUDA(cudaFuncSetAttribute(k_linear_smallm, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    k_linear_smallm<<<(unsigned)ceil_div(N, 8), 256, smem, (cudaStream_t)stream>>>(d_x, x_ld, d_w, d_bias, d_res, res_ld, d_y, y_ld, M, N, K, act);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

@@ -69,6 +69,64 @@ k_patch_embed_ln(const void* __restrict__ xin, const float* __restrict__ w, cons
     if (two) o[lane + 32] = __float2bfloat16_rn(d1 * rstd * gamma[lane + 32] + beta[lane + 32]);
 }
 
+// bf16-NHWC-input variant with the K = k*k*Cin reduction split over the 8 warps of a CTA (one CTA
+// per output token): the attention's reduction conv has K = 2048 and only 2..6 tokens per frame, so
+// a warp per token would leave the GPU idle. The patch is staged in shared memory as fp32.
+__global__ void __launch_bounds__(256)
+k_patch_embed_ln_block(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                       int H, int W, int Cin, int Cout, int k, int s, int p, int OH, int OW, float eps) {
+    extern __shared__ float s_patch[];            // [K] then [8][64] partial sums
+    const int K = k * k * Cin;
+    float* s_part = s_patch + K;
+    const long long tok = blockIdx.x;
+    const int ow = (int)(tok % OW), oh = (int)((tok / OW) % OH);
+    const long long b = tok / ((long long)OW * OH);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const int ci = i % Cin, t = i / Cin;
+        const int ih = oh * s - p + t / k, iw = ow * s - p + t % k;
+        float v = 0.f;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) v = bf2f(x[((b * H + ih) * (long long)W + iw) * Cin + ci]);
+        s_patch[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool two = Cout > 32;
+    float a0 = 0.f, a1 = 0.f;
+    const int per = (K + 7) / 8;
+    const int k_end = min(K, (warp + 1) * per);
+#pragma unroll 4
+    for (int i = warp * per; i < k_end; ++i) {
+        const float v = s_patch[i];
+        a0 = fmaf(v, __ldg(w + (long long)i * Cout + lane), a0);
+        if (two) a1 = fmaf(v, __ldg(w + (long long)i * Cout + lane + 32), a1);
+    }
+    s_part[warp * 64 + lane] = a0;
+    s_part[warp * 64 + 32 + lane] = a1;
+    __syncthreads();
+    if (warp == 0) {
+        a0 = bias[lane];
+        a1 = two ? bias[lane + 32] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            a0 += s_part[q * 64 + lane];
+            a1 += s_part[q * 64 + 32 + lane];
+        }
+        float sum = a0 + a1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        const float mean = sum / (float)Cout;
+        const float d0 = a0 - mean, d1 = two ? a1 - mean : 0.f;
+        float var = d0 * d0 + d1 * d1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+        const float rstd = rsqrtf(var / (float)Cout + eps);
+        __nv_bfloat16* o = out + tok * Cout;
+        o[lane] = __float2bfloat16_rn(d0 * rstd * gamma[lane] + beta[lane]);
+        if (two) o[lane + 32] = __float2bfloat16_rn(d1 * rstd * gamma[lane + 32] + beta[lane + 32]);
+    }
+}
+
 // LayerNorm over C (32 or 64) of bf16 rows, one warp per row
 __global__ void __launch_bounds__(256)
 k_layernorm_bf16(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -259,8 +317,14 @@ extern "C" int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, con
     const unsigned grid = (unsigned)ceil_div(total, 8);
     if (x_is_f32_nchw)
         k_patch_embed_ln<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), B, H, W, Cin, Cout, k, stride, pad, OH, OW, eps);
-    else
-        k_patch_embed_ln<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), B, H, W, Cin, Cout, k, stride, pad, OH, OW, eps);
+    else {
+        const size_t smem = ((size_t)k * k * Cin + 8 * 64) * sizeof(float);
+        EVFLY_REQUIRE(smem <= 48 * 1024, "patch_embed_ln_bf16: patch of %d values does not fit shared memory", k * k * Cin);
+        EVFLY_REQUIRE(total < (1ll << 31), "patch_embed_ln_bf16: too many tokens");
+        k_patch_embed_ln_block<<<(unsigned)total, 256, smem, (cudaStream_t)stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(d_x), d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), H, W, Cin, Cout,
+            k, stride, pad, OH, OW, eps);
+    }
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

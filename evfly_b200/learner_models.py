@@ -447,7 +447,8 @@ class OrigUNet(PackedModule):
         else:
             y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_fp32(im, x[2][0], pk)
 
-        y_vel = torch.tensor([1., 0., 0.], device=dev).repeat(N, 1)   # default: forward, full speed
+        y_vel = torch.zeros((N, 3), dtype=torch.float32, device=dev)   # default [1,0,0]: forward, full speed
+        y_vel[:, 0] = 1.0
         h_velpred = None
         if self.velpred > 0:
             src = {1: y_interp, 11: y_upconv, 2: y_e5_nchw}[self.velpred]

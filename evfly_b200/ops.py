@@ -59,6 +59,12 @@ def linear(x2d, w, bias=None, *, act=None, res2d=None, out2d=None):
     Nout = w.shape[0]
     if out2d is None:
         out2d = torch.empty((M, Nout), dtype=torch.float32, device=x2d.device)
+    if M <= 8 and x2d.stride(1) == 1 and out2d.stride(1) == 1 and (res2d is None or res2d.stride(1) == 1) and M * K * 4 <= 160 * 1024:
+        _lib.check(_lib.load().evfly_linear_smallm_f32(
+            x2d.data_ptr(), x2d.stride(0), _lib.ptr(w), _lib.ptr(bias), None if res2d is None else res2d.data_ptr(),
+            0 if res2d is None else res2d.stride(0), out2d.data_ptr(), out2d.stride(0), M, Nout, K, ACT[act], _lib.stream_ptr()),
+            "evfly_linear_smallm_f32")
+        return out2d
     as4 = lambda t: t.as_strided((1, t.shape[1], 1, t.shape[0]), (0, t.stride(1), 0, t.stride(0)), t.storage_offset())
     conv2d(as4(x2d), w.reshape(Nout, K, 1, 1), bias, act=act,
            res_view=None if res2d is None else as4(res2d), out_view=as4(out2d))

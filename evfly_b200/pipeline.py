@@ -62,6 +62,80 @@ class PerceptionPipeline:
         return vel, depth, counts, voxel
 
 
+class StreamingSession:
+    """Batch-1 streaming (BASELINE config 5, evfly_ros/run.py's 15-30 Hz loop): one window of events
+    -> velocity command, with the whole device-side step (accumulate -> decode/crop -> percentile
+    scale -> UNet/ConvLSTM -> ViT-LSTM, recurrent state carried) captured ONCE in a CUDA graph and
+    replayed per window, so the ~200 kernel launches cost one graph launch.
+
+    Event counts vary per window while a graph's kernel arguments are frozen, so the graph always
+    scatters `capacity` records from a static buffer whose tail holds skip records (polarity 2)."""
+
+    def __init__(self, pipe: "PerceptionPipeline", capacity: int = 131072, window_ns: int = 33_333_333, want_voxel: bool = True):
+        self.pipe, self.cap = pipe, int(capacity)
+        dev = pipe.dev
+        skip = torch.zeros((self.cap, 16), dtype=torch.uint8, device=dev)
+        skip[:, 12] = _lib.POL_SKIP
+        self._skip = skip
+        self.records = skip.clone()
+        self._n_prev = 0
+        self.edges = torch.tensor([0, window_ns], dtype=torch.int64, device=dev)
+        self.want_voxel = want_voxel
+        m = pipe.model
+        self.h_unet = torch.zeros((1, 512, 8, 13), dtype=torch.float32, device=dev)
+        self.c_unet = torch.zeros_like(self.h_unet)
+        self.h_vit = torch.zeros((3, 128), dtype=torch.float32, device=dev)
+        self.c_vit = torch.zeros_like(self.h_vit)
+        self.desvel = torch.full((1, 1), pipe.desvel, dtype=torch.float32, device=dev)
+        self.graph = None
+        self._capture()
+
+    def _step(self):
+        frames, counts, voxel = self.pipe.frames_from_windows(self.records, self.edges, self.want_voxel, sorted_by_time=False)
+        vel, (depth, _, ((hu, _), hv)) = self.pipe.model([frames, self.desvel, [[[self.h_unet, self.c_unet]], None], (self.h_vit, self.c_vit)])
+        self.h_unet.copy_(hu[0][0]); self.c_unet.copy_(hu[0][1])
+        self.h_vit.copy_(hv[0]); self.c_vit.copy_(hv[1])
+        return vel, depth, counts, voxel
+
+    def _capture(self):
+        with torch.no_grad():
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):          # warm-up: packs weights, sets kernel attributes, sizes the allocator
+                    self._step()
+            torch.cuda.current_stream().wait_stream(s)
+            self.reset()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.vel, self.depth, self.counts, self.voxel = self._step()
+            self.reset()
+
+    def reset(self):
+        for t in (self.h_unet, self.c_unet, self.h_vit, self.c_vit):
+            t.zero_()
+
+    def load_events(self, records: torch.Tensor, t0_ns: int = 0, window_ns: int | None = None):
+        """records uint8 [n,16] (device or pinned host); n <= capacity. Window = [t0, t0 + window)."""
+        n = records.shape[0]
+        if n > self.cap:
+            raise _lib.EvflyError(f"window of {n} events exceeds the session capacity {self.cap}")
+        self.records[:n].copy_(records, non_blocking=True)
+        if n < self._n_prev:
+            self.records[n:self._n_prev].copy_(self._skip[n:self._n_prev])
+        self._n_prev = n
+        if t0_ns != 0 or window_ns is not None:
+            w = int(self.edges[1] - self.edges[0]) if window_ns is None else window_ns
+            self.edges.copy_(torch.tensor([t0_ns, t0_ns + w], dtype=torch.int64), non_blocking=True)
+
+    def step(self, records: torch.Tensor | None = None, **kw) -> torch.Tensor:
+        """One window -> velocity command [1,3] (device tensor, valid until the next step)."""
+        if records is not None:
+            self.load_events(records, **kw)
+        self.graph.replay()
+        return self.vel
+
+
 def build_deployed_model(device="cuda", seed_state_dict=None, logger=None):
     """OrigUNet_w_VITFLY_ViTLSTM in the shipped configuration (learner/configs/eval_config_real.txt:39-47:
     bev=2, skip_type=interp, num_recurrent=[1,0], resize_input=[260,346], velpred=0)."""

@@ -223,6 +223,12 @@ typedef struct evfly_conv2d_args {
 } evfly_conv2d_args;
 int evfly_conv2d_f32(const evfly_conv2d_args* args, void* stream);
 
+/* y[m,n] = act(sum_k x[m,k] w[n,k] + bias[n]) (+ res[m,n]) for M <= 8 rows (batch-1 streaming):
+ * one warp per output feature streams its weight row once. Rows of x / res / y may be strided.  */
+int evfly_linear_smallm_f32(const float* d_x, int64_t x_ld, const float* d_w, const float* d_bias,
+                            const float* d_res, int64_t res_ld, float* d_y, int64_t y_ld, int M, int N,
+                            int K, int act, void* stream);
+
 /* 2-D pooling without padding, floor mode, on contiguous [planes,H,W] -> [planes,OH,OW].
  * mode 0 = max, 1 = average. negate_in computes pool(-x) (the reference's min-pool idiom,
  * vitfly_models.py:58 / learner_models.py:76-93), negate_out negates the result.            */
