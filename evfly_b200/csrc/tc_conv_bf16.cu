@@ -128,6 +128,8 @@ struct TcArgs {
     const float* bias;     // fp32 [bias_len] or nullptr; indexed by (n % bias_mod)
     const float* res;      // fp32 [M_rows, n_rows] or nullptr, added before the activation
     const __nv_bfloat16* res16;  // bf16 [M_rows, n_rows] or nullptr (token residuals)
+    float* lstm_c;               // ConvLSTM fused cell update: fp32 c [M_rows, n_rows/4] in/out
+    __nv_bfloat16* lstm_h;       //   and bf16 h [M_rows, n_rows/4] out; GEMM column n = 4*ch + gate (i,f,o,g)
     __nv_bfloat16* out;    // bf16 destination
     float* out_f32;        // optional fp32 destination instead (same addressing)
     long long M_rows;      // rows of the source pitch grid
@@ -331,6 +333,30 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
                     const int ncols = min(32, p.n_rows - n_first);
+                    if (p.lstm_c) {
+                        // columns [n_first, n_first+32) = 8 channels x {i,f,o,g}: the whole cell update
+                        // happens here, the gate pre-activations never go to memory (convlstm.py:44-53)
+                        const int Ch = p.n_rows >> 2, ch0l = n_first >> 2;
+                        float* cp = p.lstm_c + m * (long long)Ch + ch0l;
+                        const float4 c_lo = *reinterpret_cast<const float4*>(cp), c_hi = *reinterpret_cast<const float4*>(cp + 4);
+                        const float cin[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+                        float cn[8], hn[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float ig = 1.f / (1.f + __expf(-v[4 * q])), fg = 1.f / (1.f + __expf(-v[4 * q + 1]));
+                            const float og = 1.f / (1.f + __expf(-v[4 * q + 2]));
+                            cn[q] = fg * cin[q] + ig * tanhf(v[4 * q + 3]);
+                            hn[q] = og * tanhf(cn[q]);
+                        }
+                        *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                        *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(hn[0], hn[1]), t1 = __floats2bfloat162_rn(hn[2], hn[3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(hn[4], hn[5]), t3 = __floats2bfloat162_rn(hn[6], hn[7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(p.lstm_h + m * (long long)Ch + ch0l) = pk;
+                    } else
                     if (p.out_f32) {
                         float* o = p.out_f32 + dst_pix * p.out_ld + p.out_c0 + ch0;
                         if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -444,7 +470,9 @@ using namespace evfly;
 extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) {
     EVFLY_REQUIRE(args, "tc_conv_bf16: null args");
     const evfly_tc_conv_args a = *args;
-    EVFLY_REQUIRE(a.x && a.w && (a.out || a.out_f32), "tc_conv_bf16: null tensor");
+    EVFLY_REQUIRE(a.x && a.w && (a.out || a.out_f32 || a.lstm_c), "tc_conv_bf16: null tensor");
+    EVFLY_REQUIRE((a.lstm_c == nullptr) == (a.lstm_h == nullptr), "tc_conv_bf16: lstm_c / lstm_h go together");
+    EVFLY_REQUIRE(!a.lstm_c || (a.n_rows % 32 == 0 && !a.convt && !a.relu), "tc_conv_bf16: fused ConvLSTM needs n_rows %% 32 == 0");
     EVFLY_REQUIRE(a.M_rows > 0 && a.M_rows < (1ll << 31) && a.Cin > 0 && a.n_rows > 0 && a.n_rows <= 2048, "tc_conv_bf16: bad shape (n_rows <= 2048)");
     EVFLY_REQUIRE(a.taps == 1 || a.taps == 9, "tc_conv_bf16: taps must be 1 or 9");
     EVFLY_REQUIRE(a.Cin % 32 == 0, "tc_conv_bf16: Cin must be a multiple of 32 (got %d)", a.Cin);
@@ -456,6 +484,8 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     p.bias = a.bias;
     p.res = a.res_f32;
     p.res16 = reinterpret_cast<const __nv_bfloat16*>(a.res_bf16);
+    p.lstm_c = a.lstm_c;
+    p.lstm_h = reinterpret_cast<__nv_bfloat16*>(a.lstm_h);
     p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
     p.out_f32 = a.out_f32;
     p.M_rows = a.M_rows;

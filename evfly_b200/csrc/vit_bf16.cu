@@ -268,9 +268,11 @@ k_lstm_seq_smemw(const float* __restrict__ gx, const __nv_bfloat162* __restrict_
     }
     __syncthreads();
     const int r = threadIdx.x;
+    float gx_next = (r < G && T > 0) ? gx[r] : 0.f;
     for (int t = 0; t < T; ++t) {
         if (r < G) {
-            float acc0 = gx[(long long)t * G + r], acc1 = 0.f;
+            float acc0 = gx_next, acc1 = 0.f;
+            if (t + 1 < T) gx_next = gx[(long long)(t + 1) * G + r];   // hide the L2 latency behind this step's dot product
 #pragma unroll 8
             for (int j2 = 0; j2 < H / 2; ++j2) {
                 const float2 wv = __bfloat1622float2(s_w[j2 * G + r]);

@@ -287,7 +287,8 @@ class OrigUNet(PackedModule):
             bf["lstm"] = []
             for cell in self.lstm.cell_list:
                 w = cell.conv.weight
-                bf["lstm"].append((tc.pack_conv1x1_weight(w[:, :cell.input_dim]), tc.pack_conv1x1_weight(w[:, cell.input_dim:])))
+                w2 = w.reshape(w.shape[0], -1)      # 1x1 kernel; rows gate-major -> interleaved (fused cell epilogue)
+                bf["lstm"].append((tc.pack_convlstm_gate_weight(w2[:, :cell.input_dim]), tc.pack_convlstm_gate_weight(w2[:, cell.input_dim:])))
         pk["bf16"] = bf
         return pk
 
@@ -418,9 +419,8 @@ class OrigUNet(PackedModule):
             hview = out.data.view(T, P, Ch)
             gxv = gx.view(T, P, 4 * Ch)
             h_prev = h0
-            for t in range(T):
-                tc.gemm(h_prev, wh, None, out_f32=gxv[t], res_f32=gxv[t])
-                tc.convlstm_pointwise(gxv[t], c, hview[t])
+            for t in range(T):      # one launch per step: h-gates GEMM + x-gates + cell update
+                tc.convlstm_step(h_prev, wh, gxv[t], c, hview[t])
                 h_prev = hview[t]
             h_last = tc.grid_to_nchw(hview[T - 1].view(1, Hp, Wp, Ch), g.vh, g.vw)
             c_last = torch.empty((1, Ch, g.vh, g.vw), dtype=torch.float32, device=dev)

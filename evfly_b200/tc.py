@@ -94,6 +94,26 @@ def gemm(x2d, w_packed, bias=None, relu=False, out2d=None, out_f32=None, res_f32
     return ret
 
 
+def pack_convlstm_gate_weight(w2d: torch.Tensor) -> torch.Tensor:
+    """[4*Ch, K] with rows gate-major (i,f,o,g blocks, convlstm.py:44) -> bf16 rows interleaved n = 4*ch + gate,
+    so that one 32-column epilogue slab holds all four gates of 8 channels."""
+    G, K = w2d.shape
+    Ch = G // 4
+    return w2d.reshape(4, Ch, K).permute(1, 0, 2).reshape(G, K).to(BF16).contiguous()
+
+
+def convlstm_step(h_prev, wh_packed, gx_t, c_f32, h_out):
+    """One ConvLSTM step in ONE launch: gates = h_prev @ Wh^T + gx_t (fp32, gate-interleaved), cell update in
+    the epilogue. h_prev / h_out bf16 [P,Ch], c fp32 [P,Ch] in place."""
+    P, Ch = c_f32.shape
+    a = _lib.TcConvArgs()
+    a.x, a.w, a.res_f32 = h_prev.data_ptr(), wh_packed.data_ptr(), gx_t.data_ptr()
+    a.lstm_c, a.lstm_h = c_f32.data_ptr(), h_out.data_ptr()
+    a.M_rows, a.out_ld = P, 4 * Ch
+    a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = Ch, 4 * Ch, 1, 0, 0, 0
+    _call(a)
+
+
 def conv_transpose2x2(g: Grid, w_packed, bias, out_data: torch.Tensor, out_c0: int):
     """ConvTranspose2d(k=2,s=2) of the valid region into channels [out_c0, out_c0+Cout) of the
     compact grid out_data [N, 2*vh, 2*vw, Ctot]."""
@@ -216,3 +236,16 @@ def pack_lstm_whh_pairs(w_hh: torch.Tensor) -> torch.Tensor:
     """W_hh [4H,H] -> bf16 [H/2, 4H, 2] = {W[r][2j], W[r][2j+1]} at [j][r]."""
     G, H = w_hh.shape
     return w_hh.t().reshape(H // 2, 2, G).permute(0, 2, 1).to(BF16).contiguous()
+
+
+def gemm_into_f32(x2d, w_packed, bias, out_buf, out_c0):
+    """bf16 [M,K] @ [N,K]^T + bias -> fp32 columns [out_c0, out_c0+N) of the row-major buffer out_buf [M, ld]."""
+    M, K = x2d.shape
+    Nn = w_packed.shape[0]
+    assert x2d.is_contiguous() and x2d.dtype == BF16 and out_buf.dtype == torch.float32 and out_buf.is_contiguous()
+    a = _lib.TcConvArgs()
+    a.x, a.w, a.bias, a.out_f32 = x2d.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out_buf.data_ptr()
+    a.M_rows, a.out_ld = M, out_buf.shape[1]
+    a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = K, Nn, 1, 0, 0, out_c0
+    _call(a)
+    return out_buf

@@ -100,7 +100,8 @@ class LSTMNetVIT(_ViTEncoder):
         self._build_tail()
 
     def _pack(self):
-        return {"decoder": sn_effective_weight(self.decoder), "fc2": sn_effective_weight(self.nn_fc2), "lstm": pack_lstm(self.lstm)}
+        dec = sn_effective_weight(self.decoder)
+        return {"decoder": dec, "decoder_bf16": dec.to(tc.BF16).contiguous(), "fc2": sn_effective_weight(self.nn_fc2), "lstm": pack_lstm(self.lstm)}
 
     def forward(self, X):
         X = _inputs(self, X)
@@ -108,7 +109,10 @@ class LSTMNetVIT(_ViTEncoder):
         N = X[0].shape[0]
         feat = self._encode(X[0])
         seq, feat_out = _meta_concat(512, [(X[1], 1.0, 10.0), (X[2], 1.0, 1.0)], N, feat.device)   # X[1]/10
-        ops.linear(feat, pk["decoder"], self.decoder.bias, out2d=feat_out)
+        if self.precision == 'bf16' and N >= 16:      # [N,4608] x [4608,512] on the tensor cores, fp32 out into the concat buffer
+            tc.gemm_into_f32(feat.to(tc.BF16), pk["decoder_bf16"], self.decoder.bias, seq, 0)
+        else:
+            ops.linear(feat, pk["decoder"], self.decoder.bias, out2d=feat_out)
         state = X[3] if len(X) > 3 else None
         out, h = run_lstm(ops, pk["lstm"], seq, state, 128, smem_weights=self.precision == 'bf16')
         out = ops.linear(out, pk["fc2"], self.nn_fc2.bias)

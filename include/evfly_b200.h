@@ -322,6 +322,12 @@ typedef struct evfly_tc_conv_args {
     const void*  res_bf16;   /* optional bf16 [M_rows, n_rows] residual (x + attn(x), x + ffn(x)) */
     int32_t out_gelu;        /* reserved, must be 0 */
     int32_t reserved;
+    /* fused ConvLSTM cell (convlstm.py:44-53): with weight rows interleaved as n = 4*ch + gate
+     * (gate order i,f,o,g) the epilogue computes c = sig(f)*c + sig(i)*tanh(g), h = sig(o)*tanh(c)
+     * in place on lstm_c fp32 [M_rows, n_rows/4] and writes h as bf16 [M_rows, n_rows/4]; the gate
+     * pre-activations (GEMM + res_f32 x-gates) never reach memory. out / out_f32 are ignored.      */
+    float*       lstm_c;
+    void*        lstm_h;
 } evfly_tc_conv_args;
 int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream);
 

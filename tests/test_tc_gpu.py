@@ -174,3 +174,19 @@ def test_lstm_smem_weights(cuda_lib):
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-2, atol=3e-3)
     np.testing.assert_allclose(h.cpu().numpy(), hn.numpy(), rtol=2e-2, atol=3e-3)
     np.testing.assert_allclose(c.cpu().numpy(), cn.numpy(), rtol=2e-2, atol=3e-3)
+
+
+def test_fused_convlstm_step(cuda_lib):
+    P, Ch = 204, 512
+    h_prev, wh = bf(rnd(P, Ch, seed=1) * 0.5), bf(rnd(4 * Ch, Ch, seed=2, scale=Ch ** -0.5))
+    gx, c = rnd(P, 4 * Ch, seed=3), rnd(P, Ch, seed=4)
+    gates = h_prev.double() @ wh.double().t() + gx.double()
+    i, f, o, g = gates.split(Ch, dim=1)                       # gate-major (convlstm.py:44)
+    cn = torch.sigmoid(f) * c.double() + torch.sigmoid(i) * torch.tanh(g)
+    hn = torch.sigmoid(o) * torch.tanh(cn)
+    # device: rows / columns interleaved n = 4*ch + gate
+    inter = lambda t2d: t2d.reshape(-1, 4, Ch).permute(0, 2, 1).reshape(-1, 4 * Ch).contiguous()
+    dc, dh = c.clone().cuda(), torch.empty((P, Ch), dtype=BF, device="cuda")
+    tc.convlstm_step(h_prev.to(BF).cuda(), tc.pack_convlstm_gate_weight(wh.cuda()), inter(gx).cuda(), dc, dh)
+    np.testing.assert_allclose(dc.cpu().double().numpy(), cn.numpy(), rtol=2e-3, atol=2e-3)
+    check_bf16(dh, hn, "fused convlstm h")
