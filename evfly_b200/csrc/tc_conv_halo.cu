@@ -1,0 +1,276 @@
+// tc_conv_halo.cu -- 3x3 valid convolution for the SMALL-CHANNEL UNet layers (Cin, Cout <= 64:
+// unet_e12, e21, e22, d32, d41, d42 -- the big-spatial half of the FLOPs) on the tensor cores with the
+// input halo reused from shared memory.
+//
+// k_tc_conv_bf16 feeds every tap of every tile with its own TMA box, 9x the input traffic; at 32-64
+// channels a tap's MMA work (32-128 cycles) is far below the cost of issuing its 128 TMA row
+// requests, so those layers were TMA-request bound (168-400 TFLOP/s). Here one output tile is a
+// 16x8 pixel block; its 18x10 halo is ONE 4-D TMA box [1, 18, 10, Cin] (180 rows of 64/128 B in
+// shared memory, pixel x fastest) and each of the 9 taps is read by tcgen05.mma through a descriptor
+// that STARTS at row (kh*10 + kw) with an 8-row-group stride of 10 rows (SBO = 10 * row bytes): the
+// 128 A rows of tap (kh,kw) are exactly the pixels (r+kh, c+kw), r<16, c<8. The swizzle is applied on
+// absolute smem address bits, so shifted starts are exact (evfly_tc_shift_probe). The weights
+// (9 x Cout x Cin bf16, <= 72 KB) are loaded once per CTA and stay resident.
+//
+// warp 0 lane 0: TMA producer (halo ring) | warp 1 lane 0: MMA issuer | warp 2: TMEM alloc |
+// warps 4-7: epilogue (+bias, ReLU, bf16, masked 64/128-byte stores to the valid pixels of the grid)
+#include "tc_common.cuh"
+
+namespace evfly {
+
+struct HaloArgs {
+    const float* bias;
+    __nv_bfloat16* out;   // [N, Hp, Wp, COUT], same pitch as the input
+    int N, Hp, Wp, out_vh, out_vw;
+    int tiles_x, tiles_y;
+    int relu;
+};
+
+template <int CIN, int COUT>
+struct HaloCfg {
+    static constexpr int ROW_B = CIN * 2;                       // bytes per pixel row in smem
+    static constexpr int HALO_ROWS = 18 * 10;
+    static constexpr int HALO_BYTES = ((HALO_ROWS * ROW_B + 1023) / 1024) * 1024;
+    static constexpr int W_TAP_BYTES = COUT * ROW_B;
+    static constexpr int W_BYTES = 9 * W_TAP_BYTES;
+    static constexpr int STAGES = 4;
+    static constexpr int NACC = 4;
+    static constexpr int TMEM_COLS = (NACC * COUT <= 128) ? 128 : 256;
+    static constexpr int SMEM_BYTES = W_BYTES + STAGES * HALO_BYTES + 1024 + 512;
+    static constexpr uint32_t LAYOUT = (CIN == 64) ? kLayoutSw128 : kLayoutSw64;
+    static constexpr uint32_t SBO_A = 10 * ROW_B;               // next 8-pixel group = next output row = 10 halo rows
+    static constexpr uint32_t SBO_B = 8 * ROW_B;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256, 1)
+k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloArgs p) {
+    using Cfg = HaloCfg<CIN, COUT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                                  // [9][COUT][CIN] swizzled per tap
+    uint8_t* s_halo = smem + Cfg::W_BYTES;                // [STAGES][180][CIN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_halo + Cfg::STAGES * Cfg::HALO_BYTES);
+    uint64_t* full_bar = bars;                            // [STAGES]
+    uint64_t* empty_bar = bars + Cfg::STAGES;             // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;         // [NACC]
+    uint64_t* tempty_bar = tfull_bar + Cfg::NACC;         // [NACC]
+    uint64_t* w_bar = tempty_bar + Cfg::NACC;             // [1]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(w_bar + 2);  // [COUT]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
+    const long long total_tiles = tiles_per_img * p.N;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < Cfg::NACC; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    if (threadIdx.x < COUT) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        mbar_expect_tx(w_bar, Cfg::W_BYTES);
+        for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * Cfg::W_TAP_BYTES, &map_w, w_bar, t * CIN, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n = (int)(tile / tiles_per_img);
+            const int rem = (int)(tile - (long long)n * tiles_per_img);
+            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::HALO_ROWS * Cfg::ROW_B);
+            tma_load_4d(s_halo + stage * Cfg::HALO_BYTES, &map_x, &full_bar[stage], 0, tx * 8, ty * 16, n);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+        mbar_wait(w_bar, 0);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const uint32_t w_base = smem_u32(s_w);
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * COUT);
+            const uint32_t halo = smem_u32(s_halo + stage * Cfg::HALO_BYTES);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int kh = tap / 3, kw = tap % 3;
+                const uint32_t a0 = halo + (uint32_t)((kh * 10 + kw) * Cfg::ROW_B);
+                const uint32_t b0 = w_base + (uint32_t)(tap * Cfg::W_TAP_BYTES);
+#pragma unroll
+                for (int k = 0; k < CIN / 16; ++k) {
+                    const uint64_t da = make_smem_desc(a0 + k * 32, Cfg::SBO_A, Cfg::LAYOUT);
+                    const uint64_t db = make_smem_desc(b0 + k * 32, Cfg::SBO_B, Cfg::LAYOUT);
+                    umma_bf16(tmem_d, da, db, idesc, (tap | k) != 0);
+                }
+            }
+            umma_commit(&empty_bar[stage]);
+            umma_commit(&tfull_bar[acc]);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;          // tile pixel: r = row / 8, c = row % 8
+        const int r = row >> 3, c = row & 7;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n = (int)(tile / tiles_per_img);
+            const int rem = (int)(tile - (long long)n * tiles_per_img);
+            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            const int oh = ty * 16 + r, ow = tx * 8 + c;
+            const bool ok = oh < p.out_vh && ow < p.out_vw;
+            __nv_bfloat16* o = p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * COUT + c0), v);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float x = __uint_as_float(v[q * 8 + e]) + s_bias[c0 + q * 8 + e];
+                            f[e] = p.relu ? fmaxf(x, 0.f) : x;
+                        }
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        reinterpret_cast<uint4*>(o + c0)[q] = pk;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// input grid [N, Hp, Wp, C] as a 4-D tensor (C fastest), box [1, 18, 10, C]
+static int make_map_halo(CUtensorMap* map, const void* base, int N, int Hp, int Wp, int C) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return EVFLY_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, 10, 18, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = (C * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (halo) failed with CUresult %d (N=%d Hp=%d Wp=%d C=%d)", (int)r, N, Hp, Wp, C);
+        return EVFLY_ERR_CUDA;
+    }
+    return EVFLY_OK;
+}
+
+static int make_map_w(CUtensorMap* map, const void* base, int Cout, int Cin) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return EVFLY_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)Cin, (cuuint32_t)Cout};
+    cuuint32_t es[2] = {1, 1};
+    const CUtensorMapSwizzle sw = (Cin * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (halo weights) failed with CUresult %d", (int)r);
+        return EVFLY_ERR_CUDA;
+    }
+    return EVFLY_OK;
+}
+
+template <int CIN, int COUT>
+static int launch_halo(const void* x, const void* w, const HaloArgs& p, cudaStream_t st) {
+    using Cfg = HaloCfg<CIN, COUT>;
+    CUtensorMap mx, mw;
+    int rc = make_map_halo(&mx, x, p.N, p.Hp, p.Wp, CIN);
+    if (rc) return rc;
+    rc = make_map_w(&mw, w, COUT, CIN);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv3x3_halo<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * p.N;
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    k_tc_conv3x3_halo<CIN, COUT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+}  // namespace evfly
+
+using namespace evfly;
+
+extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int Hp, int Wp,
+                                          int vh, int vw, int Cin, int Cout, int relu, void* stream) {
+    EVFLY_REQUIRE(d_x && d_w && d_out && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
+    EVFLY_REQUIRE((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64), "tc_conv3x3_halo_bf16: Cin, Cout must be 32 or 64 (got %d, %d)", Cin, Cout);
+    HaloArgs p;
+    p.bias = d_bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(d_out);
+    p.N = N;
+    p.Hp = Hp;
+    p.Wp = Wp;
+    p.out_vh = vh - 2;
+    p.out_vw = vw - 2;
+    p.tiles_x = (p.out_vw + 7) / 8;
+    p.tiles_y = (p.out_vh + 15) / 16;
+    p.relu = relu;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 32 && Cout == 32) return launch_halo<32, 32>(d_x, d_w, p, st);
+    if (Cin == 32 && Cout == 64) return launch_halo<32, 64>(d_x, d_w, p, st);
+    if (Cin == 64 && Cout == 32) return launch_halo<64, 32>(d_x, d_w, p, st);
+    return launch_halo<64, 64>(d_x, d_w, p, st);
+}

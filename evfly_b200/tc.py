@@ -14,6 +14,7 @@ import torch
 from . import _lib
 
 BF16 = torch.bfloat16
+USE_HALO = True     # small-channel 3x3 convs through the halo-reuse kernel
 
 
 @dataclass
@@ -54,6 +55,10 @@ def pack_convt2x2_weight(w: torch.Tensor) -> torch.Tensor:
     return w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(BF16).contiguous()
 
 
+def _call_halo(*args):
+    _lib.check(_lib.load().evfly_tc_conv3x3_halo_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_bf16")
+
+
 def _call(a: _lib.TcConvArgs):
     _lib.check(_lib.load().evfly_tc_conv_bf16(C.byref(a), _lib.stream_ptr()), "evfly_tc_conv_bf16")
 
@@ -63,6 +68,10 @@ def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None) -> Grid
     Cout = w_packed.shape[0]
     if out is None:
         out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
+    if USE_HALO and g.C in (32, 64) and Cout in (32, 64):
+        # small-channel layers: halo reuse from shared memory, weights resident (tc_conv_halo.cu)
+        _call_halo(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C, Cout, int(relu))
+        return out
     a = _lib.TcConvArgs()
     a.x, a.w, a.bias, a.out = g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr()
     a.M_rows, a.out_ld = g.rows, Cout

@@ -388,6 +388,19 @@ int evfly_dwconv3x3_gelu_nhwc_bf16(const void* d_x, const float* d_w, const floa
 int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float* d_h0, const float* d_c0,
                          float* d_hs, float* d_hT, float* d_cT, int T, int H, void* stream);
 
+/* 3x3 valid conv + bias (+ReLU) for Cin, Cout in {32, 64} with the input halo reused from shared memory
+ * (one 4-D TMA box [18 x 10 pixels] per 16x8 output tile, all 9 taps read through shifted UMMA
+ * descriptors, weights resident): x bf16 [N,Hp,Wp,Cin] valid vh x vw, w bf16 [Cout, 9*Cin] ([Cout][tap][Cin]),
+ * out bf16 [N,Hp,Wp,Cout]; only the valid (vh-2) x (vw-2) outputs are written.                         */
+int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N,
+                               int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, void* stream);
+
+/* Hardware probe (diagnostic): D = x[shift : shift+128] @ w^T computed by tcgen05.mma from ONE TMA-loaded
+ * [136, KC] tile whose descriptor starts `shift` rows into the swizzle atom (base-offset field set when
+ * use_base_offset). x bf16 [136,KC], w bf16 [32,KC], out fp32 [128,32]. KC in {32 (64B swizzle), 64 (128B)}. */
+int evfly_tc_shift_probe(const void* d_x, const void* d_w, float* d_out, int KC, int shift,
+                         int use_base_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -190,3 +190,36 @@ def test_fused_convlstm_step(cuda_lib):
     tc.convlstm_step(h_prev.to(BF).cuda(), tc.pack_convlstm_gate_weight(wh.cuda()), inter(gx).cuda(), dc, dh)
     np.testing.assert_allclose(dc.cpu().double().numpy(), cn.numpy(), rtol=2e-3, atol=2e-3)
     check_bf16(dh, hn, "fused convlstm h")
+
+
+def test_shifted_descriptor_probe(cuda_lib):
+    """The hardware assumption of the halo-reuse conv: a UMMA descriptor may start at any row of a TMA-written
+    swizzled tile (base_offset = 0, swizzle on absolute address bits)."""
+    from evfly_b200 import _lib
+    for KC in (32, 64):
+        x, w = rnd(136, KC, seed=1).to(BF).cuda(), rnd(32, KC, seed=2).to(BF).cuda()
+        for shift in (0, 1, 2, 5, 8):
+            out = torch.empty((128, 32), device="cuda")
+            _lib.check(cuda_lib.evfly_tc_shift_probe(x.data_ptr(), w.data_ptr(), out.data_ptr(), KC, shift, 0, _lib.stream_ptr()))
+            want = x[shift:shift + 128].float() @ w.float().t()
+            assert torch.allclose(out, want, rtol=1e-4, atol=1e-4), (KC, shift)
+
+
+@pytest.mark.parametrize("N,H,W,vh,vw,Cin,Cout", [(2, 20, 24, 20, 24, 32, 32), (1, 37, 29, 35, 27, 64, 64), (3, 19, 11, 19, 11, 32, 64),
+                                                  (1, 72, 152, 72, 152, 64, 32), (2, 18, 10, 18, 10, 32, 32), (1, 5, 5, 3, 3, 64, 64)])
+def test_halo_conv_equals_reference_and_streaming_kernel(cuda_lib, N, H, W, vh, vw, Cin, Cout):
+    x = bf(rnd(N, Cin, vh, vw, seed=1))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5))
+    b = rnd(Cout, seed=3)
+    want = F.relu(F.conv2d(x.double(), w.double(), b.double()))
+    g = tc.nchw_to_grid(x.cuda(), H, W)
+    wp = tc.pack_conv3x3_weight(w.cuda())
+    out = tc.conv3x3(g, wp, b.cuda(), relu=True)
+    got = tc.grid_to_nchw(out.data, vh - 2, vw - 2)
+    check_bf16(got, want, "halo conv")
+    tc.USE_HALO = False
+    try:
+        ref = tc.grid_to_nchw(tc.conv3x3(g, wp, b.cuda(), relu=True).data, vh - 2, vw - 2)
+    finally:
+        tc.USE_HALO = True
+    assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()      # same math, different accumulation order
