@@ -62,6 +62,60 @@ class PerceptionPipeline:
         return vel, depth, counts, voxel
 
 
+class TrajectoryFeeder:
+    """End-to-end path for offline evaluation (learner/evaluation_tools.py:62-66 feeds trajectories one
+    after another from host memory): host batches of packed event records are staged through two device
+    buffers on a copy stream, so the H2D copy of trajectory i+1 overlaps the compute of trajectory i.
+
+        feeder = TrajectoryFeeder(pipe, max_events)
+        for vel in feeder.run(batches):   # batches: iterable of (pinned uint8 [n,16], edges_ns int64 device [T+1])
+            ...                           # vel: pinned host tensor [T,3], valid until the next iteration
+    """
+
+    def __init__(self, pipe: "PerceptionPipeline", max_events: int, max_windows: int):
+        dev = pipe.dev
+        self.pipe = pipe
+        self.bufs = [torch.empty((max_events, 16), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # H2D of slot finished
+        self.free = [torch.cuda.Event() for _ in range(2)]       # compute on slot finished
+        self.h_vel = [torch.empty((max_windows, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+
+    def _stage(self, slot, records):
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[slot])
+            self.bufs[slot][: records.shape[0]].copy_(records, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def run(self, batches):
+        it = iter(batches)
+        main = torch.cuda.current_stream()
+        for e in self.free:
+            e.record(main)
+        cur = next(it, None)
+        if cur is None:
+            return
+        self._stage(0, cur[0])
+        slot = 0
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                self._stage(slot ^ 1, nxt[0])          # overlaps with the compute below
+            main.wait_event(self.ready[slot])
+            n, T = cur[0].shape[0], cur[1].shape[0] - 1
+            with torch.no_grad():
+                self.pipe.reset()
+                vel, _, _, _ = self.pipe(self.bufs[slot][:n], cur[1])
+                self.h_vel[slot][:T].copy_(vel, non_blocking=True)
+            self.free[slot].record(main)
+            self.done[slot].record(main)
+            self.done[slot].synchronize()
+            yield self.h_vel[slot][:T]
+            cur, slot = nxt, slot ^ 1
+
+
 class StreamingSession:
     """Batch-1 streaming (BASELINE config 5, evfly_ros/run.py's 15-30 Hz loop): one window of events
     -> velocity command, with the whole device-side step (accumulate -> decode/crop -> percentile
