@@ -20,6 +20,7 @@
 //   warp 2        : TMEM allocator (2 accumulator buffers of TN fp32 columns)
 //   warps 4..7    : epilogue      (tcgen05.ld 32x32b -> +bias -> ReLU -> bf16 -> 16-byte stores)
 #include "tc_common.cuh"
+#include <string.h>
 
 namespace evfly {
 
@@ -33,6 +34,7 @@ struct TcArgs {
     __nv_bfloat16* out;    // bf16 destination
     float* out_f32;        // optional fp32 destination instead (same addressing)
     long long M_rows;      // rows of the source pitch grid
+    long long a_row0;      // first row of this problem inside the tensor map_a describes (ConvLSTM scan)
     int Cin, n_rows;       // K per tap; GEMM N (rows of the weight matrix)
     int taps, w_pitch;     // 1 or 9; pixels per grid row (the kh shift)
     int relu;
@@ -116,7 +118,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int kb = 0; kb < k_blocks; ++kb) {
                 const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
                 const int kh = tap / 3, kw = tap - kh * 3;  // taps == 1 -> 0,0
-                const long long row = m0 + (long long)kh * p.w_pitch + kw;
+                const long long row = p.a_row0 + m0 + (long long)kh * p.w_pitch + kw;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                 uint8_t* sb = sa + Cfg::A_BYTES;
@@ -340,6 +342,21 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
 }
 
 template <int TN, int KC>
+static int launch_tc_maps(const CUtensorMap& map_a, const CUtensorMap& map_b, const TcArgs& p, cudaStream_t st) {
+    using Cfg = TcCfg<TN, KC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv_bf16<TN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long tiles = ceil_div(p.M_rows, Cfg::BM) * ceil_div(p.n_rows, TN);
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    k_tc_conv_bf16<TN, KC><<<grid, 256, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+template <int TN, int KC>
 static int launch_tc(const evfly_tc_conv_args& a, const TcArgs& p, cudaStream_t st) {
     using Cfg = TcCfg<TN, KC>;
     CUtensorMap map_a, map_b;
@@ -347,16 +364,7 @@ static int launch_tc(const evfly_tc_conv_args& a, const TcArgs& p, cudaStream_t 
     if (rc) return rc;
     rc = make_map_2d(&map_b, a.w, (uint64_t)a.n_rows, (uint64_t)a.taps * a.Cin, (uint64_t)a.taps * a.Cin, TN, KC);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv_bf16<TN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
-    const long long tiles = ceil_div(a.M_rows, Cfg::BM) * ceil_div(a.n_rows, TN);
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    k_tc_conv_bf16<TN, KC><<<grid, 256, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
-    EVFLY_LAUNCHED();
-    return EVFLY_OK;
+    return launch_tc_maps<TN, KC>(map_a, map_b, p, st);
 }
 
 }  // namespace evfly
@@ -385,6 +393,7 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
     p.out_f32 = a.out_f32;
     p.M_rows = a.M_rows;
+    p.a_row0 = 0;
     p.Cin = a.Cin;
     p.n_rows = a.n_rows;
     p.taps = a.taps;
@@ -419,4 +428,38 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
         if (tn == 128) return launch_tc<128, 32>(a, p, st);
         return launch_tc<256, 32>(a, p, st);
     }
+}
+
+// ConvLSTM (1x1 kernel) scan over T steps in ONE call: the tensor maps are encoded once and the T fused
+// step kernels (h-gates GEMM + x-gates + cell update, see lstm_c above) are enqueued back to back from C++.
+// d_h_all bf16 [(T+1)*P, Ch]: block 0 holds h_0 on entry, block t+1 receives h_t.
+extern "C" int evfly_convlstm_scan_bf16(void* d_h_all, const void* d_wh, const float* d_gx, float* d_c, int T, int64_t P, int Ch,
+                                        void* stream) {
+    EVFLY_REQUIRE(d_h_all && d_wh && d_gx && d_c && T >= 0 && P > 0 && Ch > 0 && Ch % 64 == 0 && 4 * Ch <= 2048, "convlstm_scan_bf16: bad argument (Ch %% 64 == 0, 4*Ch <= 2048)");
+    if (T == 0) return EVFLY_OK;
+    constexpr int TN = 32, KC = 64;
+    using Cfg = TcCfg<TN, KC>;
+    CUtensorMap map_a, map_b;
+    int rc = make_map_2d(&map_a, d_h_all, (uint64_t)(T + 1) * P, (uint64_t)Ch, (uint64_t)Ch, Cfg::BM, KC);
+    if (rc) return rc;
+    rc = make_map_2d(&map_b, d_wh, (uint64_t)4 * Ch, (uint64_t)Ch, (uint64_t)Ch, TN, KC);
+    if (rc) return rc;
+    TcArgs p;
+    memset(&p, 0, sizeof(p));
+    p.M_rows = P;
+    p.Cin = Ch;
+    p.n_rows = 4 * Ch;
+    p.taps = 1;
+    p.bias_mod = 4 * Ch;
+    p.out_ld = 4 * Ch;
+    p.lstm_c = d_c;
+    __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(d_h_all);
+    for (int t = 0; t < T; ++t) {
+        p.a_row0 = (long long)t * P;
+        p.res = d_gx + (long long)t * P * 4 * Ch;
+        p.lstm_h = h + (long long)(t + 1) * P * Ch;
+        rc = launch_tc_maps<TN, KC>(map_a, map_b, p, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return EVFLY_OK;
 }

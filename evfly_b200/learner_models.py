@@ -399,8 +399,9 @@ class OrigUNet(PackedModule):
 
     def _convlstm_bf16(self, g, state, Wl):
         """ConvLSTM (1x1 kernel, no bias) over the N = time axis on the pitch grid: the x half of the
-        gate conv is ONE tensor-core GEMM over all steps, the h half one small GEMM per step whose
-        epilogue adds the x gates; the cell update is a pointwise kernel (fp32 c, bf16 h)."""
+        gate conv is ONE tensor-core GEMM over all steps; the h half is one small GEMM per step whose
+        epilogue adds the x gates and performs the cell update (fp32 c, bf16 h), all T steps enqueued
+        by one C-ABI call."""
         T, Hp, Wp, dev = g.N, g.Hp, g.Wp, g.data.device
         P = Hp * Wp
         states = []
@@ -410,18 +411,16 @@ class OrigUNet(PackedModule):
             gx = torch.empty((T * P, 4 * Ch), dtype=torch.float32, device=dev)
             tc.gemm(cur.data.view(T * P, cur.C), wx, None, out_f32=gx)
             c = torch.zeros((P, Ch), dtype=torch.float32, device=dev)
-            h0 = torch.zeros((P, Ch), dtype=tc.BF16, device=dev)
+            h_all = torch.empty((T + 1, P, Ch), dtype=tc.BF16, device=dev)      # block 0 = h_0, block t+1 = h_t
             if state is not None:
                 hs, cs = to_dev(state[li][0], dev), to_dev(state[li][1], dev)        # [1,Ch,vh,vw] each
-                h0 = tc.nchw_to_grid(hs, Hp, Wp).data.view(P, Ch)
+                h_all[0].copy_(tc.nchw_to_grid(hs, Hp, Wp).data.view(P, Ch))
                 ops.map4d(cs[0].permute(1, 2, 0), c.view(Hp, Wp, Ch)[:g.vh, :g.vw])
-            out = tc.new_grid(T, Hp, Wp, Ch, g.vh, g.vw, dev)
+            else:
+                h_all[0].zero_()
+            tc.convlstm_scan(h_all, wh, gx, c, T, P, Ch)     # T fused step kernels enqueued from C++
+            out = tc.Grid(h_all[1:].view(T, Hp, Wp, Ch), g.vh, g.vw)
             hview = out.data.view(T, P, Ch)
-            gxv = gx.view(T, P, 4 * Ch)
-            h_prev = h0
-            for t in range(T):      # one launch per step: h-gates GEMM + x-gates + cell update
-                tc.convlstm_step(h_prev, wh, gxv[t], c, hview[t])
-                h_prev = hview[t]
             h_last = tc.grid_to_nchw(hview[T - 1].view(1, Hp, Wp, Ch), g.vh, g.vw)
             c_last = torch.empty((1, Ch, g.vh, g.vw), dtype=torch.float32, device=dev)
             ops.map4d(c.view(Hp, Wp, Ch)[:g.vh, :g.vw].permute(2, 0, 1), c_last[0])

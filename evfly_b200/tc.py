@@ -55,6 +55,10 @@ def pack_convt2x2_weight(w: torch.Tensor) -> torch.Tensor:
     return w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(BF16).contiguous()
 
 
+def _call_scan(*args):
+    _lib.check(_lib.load().evfly_convlstm_scan_bf16(*args, _lib.stream_ptr()), "evfly_convlstm_scan_bf16")
+
+
 def _call_halo(*args):
     _lib.check(_lib.load().evfly_tc_conv3x3_halo_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_bf16")
 
@@ -121,6 +125,11 @@ def convlstm_step(h_prev, wh_packed, gx_t, c_f32, h_out):
     a.M_rows, a.out_ld = P, 4 * Ch
     a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = Ch, 4 * Ch, 1, 0, 0, 0
     _call(a)
+
+
+def convlstm_scan(h_all, wh_packed, gx, c_f32, T, P, Ch):
+    """h_all bf16 [(T+1), P, Ch] (block 0 = h_0), gx fp32 [T*P, 4Ch], c fp32 [P,Ch]: the whole recurrence in one call."""
+    _call_scan(h_all.data_ptr(), wh_packed.data_ptr(), _lib.ptr(gx), _lib.ptr(c_f32), T, P, Ch)
 
 
 def conv_transpose2x2(g: Grid, w_packed, bias, out_data: torch.Tensor, out_c0: int):
