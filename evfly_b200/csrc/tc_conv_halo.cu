@@ -13,7 +13,8 @@
 // (9 x Cout x Cin bf16, <= 72 KB) are loaded once per CTA and stay resident.
 //
 // warp 0 lane 0: TMA producer (halo ring) | warp 1 lane 0: MMA issuer | warp 2: TMEM alloc |
-// warps 4-7: epilogue (+bias, ReLU, bf16, masked 64/128-byte stores to the valid pixels of the grid)
+// warps 4-11: epilogue in two groups of 4 warps that alternate tiles (+bias, ReLU, bf16, masked 64/128-byte
+// stores to the valid pixels): one warp per SM sub-partition was latency-bound at ~1 us per tile
 #include "tc_common.cuh"
 
 namespace evfly {
@@ -50,7 +51,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloArgs p) {
     using Cfg = HaloCfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
@@ -67,8 +68,8 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     float* s_bias = reinterpret_cast<float*>(w_bar + 2);  // [COUT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
-    const long long total_tiles = tiles_per_img * p.N;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int total_tiles = tiles_per_img * p.N;      // host guarantees < 2^31
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_x);
@@ -99,9 +100,9 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * Cfg::W_TAP_BYTES, &map_w, w_bar, t * CIN, 0);
         int stage = 0;
         uint32_t phase = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n = (int)(tile / tiles_per_img);
-            const int rem = (int)(tile - (long long)n * tiles_per_img);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n = tile / tiles_per_img;
+            const int rem = tile - n * tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], Cfg::HALO_ROWS * Cfg::ROW_B);
@@ -115,7 +116,7 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         const uint32_t w_base = smem_u32(s_w);
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
@@ -139,15 +140,20 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ================= epilogue =================
-        const int ew = warp - 4;
+        // ================= epilogue: group 0 = warps 4-7 (even local tiles), group 1 = warps 8-11 (odd) =====
+        const int ew = (warp - 4) & 3;           // TMEM lanes [32*ew, 32*ew+32) (a warp may only touch lanes of warp%4)
+        const int grp = (warp - 4) >> 2;
         const int row = ew * 32 + lane;          // tile pixel: r = row / 8, c = row % 8
         const int r = row >> 3, c = row & 7;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n = (int)(tile / tiles_per_img);
-            const int rem = (int)(tile - (long long)n * tiles_per_img);
+        float breg[COUT];                        // bias in registers (same for every tile)
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) breg[j] = s_bias[j];
+        int it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+            const int acc = it & (Cfg::NACC - 1);
+            const uint32_t acc_phase = (uint32_t)(it / Cfg::NACC) & 1u;
+            const int n = tile / tiles_per_img;
+            const int rem = tile - n * tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int oh = ty * 16 + r, ow = tx * 8 + c;
             const bool ok = oh < p.out_vh && ow < p.out_vw;
@@ -165,7 +171,7 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            float x = __uint_as_float(v[q * 8 + e]) + s_bias[c0 + q * 8 + e];
+                            const float x = __uint_as_float(v[q * 8 + e]) + breg[c0 + q * 8 + e];
                             f[e] = p.relu ? fmaxf(x, 0.f) : x;
                         }
                         uint4 pk;
@@ -180,7 +186,6 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -244,7 +249,7 @@ static int launch_halo(const void* x, const void* w, const HaloArgs& p, cudaStre
     }
     const long long tiles = (long long)p.tiles_x * p.tiles_y * p.N;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    k_tc_conv3x3_halo<CIN, COUT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
+    k_tc_conv3x3_halo<CIN, COUT><<<grid, 384, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }
@@ -268,6 +273,7 @@ extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, cons
     p.tiles_x = (p.out_vw + 7) / 8;
     p.tiles_y = (p.out_vh + 15) / 16;
     p.relu = relu;
+    EVFLY_REQUIRE((long long)p.tiles_x * p.tiles_y * N < (1ll << 31), "tc_conv3x3_halo_bf16: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 32 && Cout == 32) return launch_halo<32, 32>(d_x, d_w, p, st);
     if (Cin == 32 && Cout == 64) return launch_halo<32, 64>(d_x, d_w, p, st);
