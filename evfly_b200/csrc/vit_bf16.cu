@@ -13,12 +13,12 @@ __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float
 
 // ---------------------------------------------------------------------------------------
 // conv (k x k, stride s, pad p) + bias + LayerNorm(Cout) -> bf16 tokens [B, OH*OW, Cout]
-// one warp per output token; lane l owns channels l, l+32 (Cout <= 64). Input either fp32 NCHW
-// with Cin == 1 (the depth image) or bf16 NHWC. Weights fp32 [K][Cout], K = (kh*k + kw)*Cin + ci.
+// fp32 NCHW input with Cin == 1 (the depth image): one warp per output token; lane l owns channels
+// l, l+32 (Cout <= 64). Weights fp32 [K][Cout], K = (kh*k + kw)*Cin + ci. The bf16 NHWC-input
+// variant is k_patch_embed_ln_block below.
 // ---------------------------------------------------------------------------------------
-template <bool IN_F32>
 __global__ void __launch_bounds__(256)
-k_patch_embed_ln(const void* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ bias,
+k_patch_embed_ln(const float* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ bias,
                  const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                  int B, int H, int W, int Cin, int Cout, int k, int s, int p, int OH, int OW, float eps) {
     const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -36,22 +36,9 @@ k_patch_embed_ln(const void* __restrict__ xin, const float* __restrict__ w, cons
             const int iw = ow * s - p + kw;
             if ((unsigned)iw >= (unsigned)W) continue;
             const float* wp = w + (long long)((kh * k + kw) * Cin) * Cout;
-            if (IN_F32) {
-                const float v = __ldg(reinterpret_cast<const float*>(xin) + (b * H + ih) * (long long)W + iw);
-                a0 = fmaf(v, wp[lane], a0);
-                if (two) a1 = fmaf(v, wp[lane + 32], a1);
-            } else {
-                const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(xin) + ((b * H + ih) * (long long)W + iw) * Cin;
-                for (int c0 = 0; c0 < Cin; c0 += 32) {
-                    const float mine = bf2f(xp[c0 + lane]);  // coalesced 64-byte read, then broadcast by shuffle
-#pragma unroll 8
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = __shfl_sync(0xffffffffu, mine, j);
-                        a0 = fmaf(v, wp[(long long)(c0 + j) * Cout + lane], a0);
-                        if (two) a1 = fmaf(v, wp[(long long)(c0 + j) * Cout + lane + 32], a1);
-                    }
-                }
-            }
+            const float v = __ldg(xin + (b * H + ih) * (long long)W + iw);
+            a0 = fmaf(v, wp[lane], a0);
+            if (two) a1 = fmaf(v, wp[lane + 32], a1);
         }
     }
     // LayerNorm over Cout
@@ -318,7 +305,7 @@ extern "C" int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, con
     const long long total = (long long)B * OH * OW;
     const unsigned grid = (unsigned)ceil_div(total, 8);
     if (x_is_f32_nchw)
-        k_patch_embed_ln<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), B, H, W, Cin, Cout, k, stride, pad, OH, OW, eps);
+        k_patch_embed_ln<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(d_x), d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), B, H, W, Cin, Cout, k, stride, pad, OH, OW, eps);
     else {
         const size_t smem = ((size_t)k * k * Cin + 8 * 64) * sizeof(float);
         EVFLY_REQUIRE(smem <= 48 * 1024, "patch_embed_ln_bf16: patch of %d values does not fit shared memory", k * k * Cin);

@@ -320,8 +320,7 @@ typedef struct evfly_tc_conv_args {
     int32_t Cin, n_rows, taps, w_pitch, relu, out_c0;
     int32_t convt, Hp, Wp, valid_h, valid_w, cout_t;
     const void*  res_bf16;   /* optional bf16 [M_rows, n_rows] residual (x + attn(x), x + ffn(x)) */
-    int32_t out_gelu;        /* reserved, must be 0 */
-    int32_t reserved;
+    int64_t reserved;        /* must be 0 */
     /* fused ConvLSTM cell (convlstm.py:44-53): with weight rows interleaved as n = 4*ch + gate
      * (gate order i,f,o,g) the epilogue computes c = sig(f)*c + sig(i)*tanh(g), h = sig(o)*tanh(c)
      * in place on lstm_c fp32 [M_rows, n_rows/4] and writes h as bf16 [M_rows, n_rows/4]; the gate
