@@ -185,6 +185,22 @@ int evfly_quantile_scale_clip(const float* d_x, int N, int64_t elems_per_frame, 
                               void* stream);
 
 /* ======================================================================================
+ * "next" rows: the callers / formats either side of the path
+ * ====================================================================================== */
+
+/* N2: difflog event approximation (envtest/ros/run_competition.py:603-635, SMALL_EPS = 1e-5;
+ * utils/to_events.py:417-439 with inputs_are_log = 1): d = log(im+eps) - log(prev+eps) in float64;
+ * all zeros if max|d| < max(pos,neg), else events = (d // pos)*pos for d > 0, (d // -neg)*(-neg) for
+ * d < 0, with numpy's floor_divide semantics. d_ws8: 8 bytes of scratch.                           */
+int evfly_difflog_events_f64(const double* d_im, const double* d_prev, int64_t n, double eps,
+                             int inputs_are_log, double pos_thresh, double neg_thresh, double* d_events,
+                             void* d_ws8, void* stream);
+
+/* N1: in-place |x| < cutoff -> 0 (learner/dataloading.py:531-533); the percentile scaling itself is
+ * evfly_quantile_scale_clip.                                                                       */
+int evfly_min_cutoff_f32(float* d_x, int64_t n, float cutoff, void* stream);
+
+/* ======================================================================================
  * L3  model forward: operator entry points (fp32 exact path)
  *
  * The reference's forward is stock PyTorch (learner/learner_models.py:521-616,

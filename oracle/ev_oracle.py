@@ -217,3 +217,32 @@ def quantile_scale_clip(frames, q=0.97, lo=-1.0, hi=1.0, cutoff=0.0):
                 v = np.where(np.abs(v) < np.float32(cutoff), np.float32(0), v)
             out[i] = v
     return out.reshape(x.shape), qs
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: difflog events (run_competition.py:603-635, to_events.py:417-439), dataset normalisation
+# ---------------------------------------------------------------------------------------------
+def difflog_events(im, prev_im, neg_thresh=0.2, pos_thresh=0.2, eps=1e-5, inputs_are_log=False):
+    im, prev_im = np.asarray(im, dtype=np.float64), np.asarray(prev_im, dtype=np.float64)
+    difflog = im - prev_im if inputs_are_log else np.log(im + eps) - np.log(prev_im + eps)
+    events = np.zeros_like(difflog)
+    if np.abs(difflog).max() < max(pos_thresh, neg_thresh):
+        return events
+    pos, neg = np.where(difflog > 0.0), np.where(difflog < 0.0)
+    events[pos] = (difflog[pos] // pos_thresh) * pos_thresh
+    events[neg] = (difflog[neg] // -neg_thresh) * -neg_thresh
+    return events
+
+
+def normalize_event_frames(ev, rescale_evs=-1.0, evs_min_cutoff=None):
+    """learner/dataloading.py:508-533 for one trajectory [T,H,W], with torch like the reference."""
+    import torch
+    ev = torch.as_tensor(np.asarray(ev, dtype=np.float32)).clone()
+    if rescale_evs > 0.0:
+        ev = torch.clamp(ev / rescale_evs, -1.0, 1.0)
+    elif rescale_evs == -1.0:
+        maxvals = torch.quantile(torch.abs(ev).view(ev.shape[0], -1), 0.97, dim=1).view(ev.shape[0], 1, 1)
+        ev = torch.clamp(ev / maxvals, -1.0, 1.0)
+    if evs_min_cutoff is not None:
+        ev[ev.abs() < evs_min_cutoff] = 0.0
+    return ev.numpy()
