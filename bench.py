@@ -167,6 +167,7 @@ class PipelineWorkload:
     name = ("cfg3/4: per GPU 1 trajectory x 256 windows (260x346, 100k events each): count frames + 5-bin voxel "
             "-> prep -> UNet+ConvLSTM+ViT-LSTM forward, bf16 tensor-core path")
     H, W, B, T, N_EV = 260, 346, 5, 256, 100_000
+    N_TRAJ = 1
     windows_per_step = 256
     dtype = "bf16"
     # 2*MAC per frame measured from the reference modules
@@ -185,24 +186,28 @@ class PipelineWorkload:
         model.load_state_dict(self.sd)
         self.model = evfly_b200.set_precision(model.to(device).eval(), precision)
         self.pipe = PerceptionPipeline(self.model, sensor_hw=(self.H, self.W), model_hw=(self.H, self.W), num_bins=self.B)
-        self.host, edges = synthetic_stream(7000 + rank, self.T, self.N_EV, self.H, self.W)
-        self.edges_host = edges
-        self.pinned = torch.from_numpy(self.host.view(np.uint8).reshape(-1, 16)).pin_memory()
-        self.d_in = self.pinned.to(device)
-        self.d_stage = torch.empty_like(self.d_in)
-        self.d_edges = torch.from_numpy(edges).to(device)
-        self.h_vel = torch.empty((self.T, 3), dtype=torch.float32).pin_memory()
-        self.h2d_bytes = self.pinned.numel()
-        self.d2h_bytes = self.h_vel.numel() * 4
+        streams = [synthetic_stream(7000 + 64 * rank + s, self.T, self.N_EV, self.H, self.W) for s in range(self.N_TRAJ)]
+        self.host, self.edges_host = streams[0]
+        self.pinned_list = [torch.from_numpy(h.view(np.uint8).reshape(-1, 16)).pin_memory() for h, _ in streams]
+        self.d_in_list = [p.to(device) for p in self.pinned_list]
+        self.d_edges = torch.from_numpy(self.edges_host).to(device)
+        self.d_in = self.d_in_list[0]
+        self.h2d_bytes = sum(p.numel() for p in self.pinned_list)
+        self.d2h_bytes = self.N_TRAJ * self.T * 3 * 4
+        self.windows_per_step = self.N_TRAJ * self.T
         # work of the tcgen05 kernels: UNet convs (minus the CUDA-core stem) + ConvLSTM + the ViT Linear layers
         # (q/kv/final/mlp1/mlp2 = 54.0 MFLOP/frame of the 0.1106 G ViT-LSTM total) + decoder Linear 4.7 M
-        self.tc_flops = self.T * (self.FLOP_UNET - self.FLOP_STEM + self.FLOP_CONVLSTM + 0.0587e9)
-        self.acc_bytes = 16 * self.T * self.N_EV + self.T * self.H * self.W * 4 * (2 + self.B)
+        W_ = self.N_TRAJ * self.T
+        self.tc_flops = W_ * (self.FLOP_UNET - self.FLOP_STEM + self.FLOP_CONVLSTM + 0.0587e9)
+        self.acc_bytes = 16 * W_ * self.N_EV + W_ * self.H * self.W * 4 * (2 + self.B)
 
     def step(self, i: int):
         with self.torch.no_grad():
             self.pipe.reset()
-            self.out = self.pipe(self.d_in, self.d_edges)
+            if self.N_TRAJ == 1:
+                self.out = self.pipe(self.d_in, self.d_edges)
+            else:
+                self.out = self.pipe.run_trajectories(self.d_in_list, [self.d_edges] * self.N_TRAJ)
 
     def e2e_run(self, steps: int):
         """End to end through the public API (evfly_b200.pipeline.TrajectoryFeeder): every step's 410 MB of
@@ -211,9 +216,10 @@ class PipelineWorkload:
         are read back to the host. Returns wall seconds for `steps` steps (first copy included)."""
         from evfly_b200.pipeline import TrajectoryFeeder
         torch = self.torch
-        feeder = TrajectoryFeeder(self.pipe, self.pinned.shape[0], self.T)
-        batches = [(self.pinned, self.d_edges)] * steps
-        for _ in feeder.run([(self.pinned, self.d_edges)] * 2):      # warm-up
+        feeder = TrajectoryFeeder(self.pipe, sum(p.shape[0] for p in self.pinned_list), self.N_TRAJ * self.T)
+        one = (self.pinned_list, [self.d_edges] * self.N_TRAJ) if self.N_TRAJ > 1 else (self.pinned_list[0], self.d_edges)
+        batches = [one] * steps
+        for _ in feeder.run([one] * 2):      # warm-up
             pass
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -242,10 +248,16 @@ class PipelineWorkload:
                 self.pipe.reset()
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record()
-                frames, counts, voxel = self.pipe.frames_from_windows(self.d_in, self.d_edges)
+                fr = [self.pipe.frames_from_windows(d, self.d_edges)[0] for d in self.d_in_list]
                 a1.record()
                 self._acc_ev = getattr(self, "_acc_ev", []) + [(a0, a1)]
-                self.pipe.forward(frames)
+                if self.N_TRAJ == 1:
+                    self.pipe.forward(fr[0])
+                else:
+                    n, T = self.N_TRAJ, self.T
+                    tm = torch.stack(fr, dim=1).reshape(T * n, 1, self.H, self.W)
+                    dv = torch.full((T * n, 1), 4.0, dtype=torch.float32, device=self.dev)
+                    self.model.forward_trajectories([tm, dv, [None, None], None], n)
         finally:
             tc._call, tc._call_halo, tc._call_scan = orig, orig_halo, orig_scan
 
@@ -342,8 +354,19 @@ class PipelineWorkload:
             M.orig_unet_w_vitlstm(self.sd, torch.from_numpy(fr), torch.full((T, 1), 4.0), None, None, **M.DEPLOYED_UNET_CFG)
 
 
-WORKLOADS = {"accumulate": AccumulateWorkload, "pipeline": PipelineWorkload}
-DEFAULT_WORKLOAD = "pipeline"
+class TrajectoryEvalWorkload(PipelineWorkload):
+    """BASELINE config 4 (the multi-GPU metric's configuration): offline evaluation of independent trajectories of
+    100 windows each. Per GPU and per step, a slice of 4 trajectories (of the job's 2048, sharded r::G over the
+    ranks) = 400 windows: each trajectory's stream -> count frames + voxel grids -> normalise; the model then
+    advances the 4 trajectories together (time-major frames), so the ConvLSTM/LSTM scans are 100 steps wide-4."""
+    name = ("cfg4: per GPU 4 trajectories x 100 windows (260x346, 100k events each; slice of 2048 trajectories sharded over "
+            "ranks): count frames + 5-bin voxel -> prep -> UNet+ConvLSTM+ViT-LSTM forward, bf16 tensor-core path, "
+            "per-trajectory recurrent state")
+    T, N_TRAJ = 100, 4
+
+
+WORKLOADS = {"accumulate": AccumulateWorkload, "pipeline": PipelineWorkload, "trajectories": TrajectoryEvalWorkload}
+DEFAULT_WORKLOAD = "trajectories"
 
 
 # =============================================================================================

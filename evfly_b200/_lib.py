@@ -69,7 +69,7 @@ SIGNATURES.update({
     "evfly_map4d_f32": (_i32, [_vp, _p64, _vp, _p64, _p64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "evfly_pixel_shuffle_f32": (_i32, [_vp, _p64, _vp, _p64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_form_input_f32": (_i32, [_vp, _vp, _i64, _i64, _i32, _f32, _vp]),
-    "evfly_lstm_seq_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "evfly_lstm_seq_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "evfly_convlstm_pointwise_f32": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "evfly_velpred_unit_f32": (_i32, [_vp, _vp, _i32, _vp]),
 })
@@ -101,7 +101,7 @@ SIGNATURES.update({
     "evfly_dwconv3x3_gelu_nhwc_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "evfly_tc_conv3x3_halo_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_tc_shift_probe": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
-    "evfly_lstm_seq_smemw": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "evfly_lstm_seq_smemw": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
 })
 
 ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "gelu": 3, "tanh": 4, "sigmoid": 5}

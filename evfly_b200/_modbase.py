@@ -89,34 +89,31 @@ def pack_lstm(lstm: nn.LSTM):
     return layers
 
 
-def run_lstm(ops, packed_layers, seq, state, hidden, smem_weights=False):
-    """nn.LSTM forward on an unbatched sequence seq [T,in] with state (h0,c0) [L,H] or None.
-    Returns (out [T,H], (h [L,H], c [L,H]))."""
+def run_lstm(ops, packed_layers, seq, state, hidden, smem_weights=False, n_seq=1):
+    """nn.LSTM forward on an unbatched sequence seq [T,in] with state (h0,c0) [L,H] or None
+    -> (out [T,H], (h [L,H], c [L,H])).
+    n_seq > 1 (extension for trajectory batches): seq is the time-major batch [T*n_seq, in] (row t*n_seq + s),
+    states are [L, n_seq, H] like PyTorch's batched LSTM, out is [T*n_seq, H]; one CTA per sequence."""
     L = len(packed_layers)
     dev = seq.device
-    h_out = torch.empty((L, hidden), dtype=torch.float32, device=dev)
-    c_out = torch.empty((L, hidden), dtype=torch.float32, device=dev)
+    st_shape = (L, hidden) if n_seq == 1 else (L, n_seq, hidden)
+    h_out = torch.empty(st_shape, dtype=torch.float32, device=dev)
+    c_out = torch.empty(st_shape, dtype=torch.float32, device=dev)
     h0 = c0 = None
     if state is not None:
         h0, c0 = to_dev(state[0], dev), to_dev(state[1], dev)
+        assert tuple(h0.shape) == st_shape and tuple(c0.shape) == st_shape, "LSTM state shape"
     lib = _lib.load()
     inp = seq
     for l, (w_ih, b, w_hh_t, pairs) in enumerate(packed_layers):
         gx = ops.linear(inp, w_ih, b)
-        T = gx.shape[0]
-        hs = torch.empty((T, hidden), dtype=torch.float32, device=dev)
+        T = gx.shape[0] // n_seq
+        hs = torch.empty((T * n_seq, hidden), dtype=torch.float32, device=dev)
+        args = (None if h0 is None else h0[l].data_ptr(), None if c0 is None else c0[l].data_ptr(),
+                _lib.ptr(hs), h_out[l].data_ptr(), c_out[l].data_ptr(), T, hidden, n_seq, _lib.stream_ptr())
         if smem_weights and pairs is not None and T >= 16:     # bf16 W_hh resident in shared memory (bf16 path, long sequences)
-            _lib.check(lib.evfly_lstm_seq_smemw(_lib.ptr(gx), pairs.data_ptr(),
-                                                None if h0 is None else h0[l].data_ptr(),
-                                                None if c0 is None else c0[l].data_ptr(),
-                                                _lib.ptr(hs), h_out[l].data_ptr(), c_out[l].data_ptr(), T, hidden,
-                                                _lib.stream_ptr()), "evfly_lstm_seq_smemw")
-            inp = hs
-            continue
-        _lib.check(lib.evfly_lstm_seq_f32(_lib.ptr(gx), _lib.ptr(w_hh_t),
-                                          None if h0 is None else h0[l].data_ptr(),
-                                          None if c0 is None else c0[l].data_ptr(),
-                                          _lib.ptr(hs), h_out[l].data_ptr(), c_out[l].data_ptr(), T, hidden,
-                                          _lib.stream_ptr()), "evfly_lstm_seq_f32")
+            _lib.check(lib.evfly_lstm_seq_smemw(_lib.ptr(gx), pairs.data_ptr(), *args), "evfly_lstm_seq_smemw")
+        else:
+            _lib.check(lib.evfly_lstm_seq_f32(_lib.ptr(gx), _lib.ptr(w_hh_t), *args), "evfly_lstm_seq_f32")
         inp = hs
     return inp, (h_out, c_out)

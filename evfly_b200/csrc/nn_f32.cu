@@ -388,8 +388,18 @@ k_form_input(float* __restrict__ x, float* __restrict__ out, long long n, long l
 __global__ void __launch_bounds__(1024)
 k_lstm_seq(const float* __restrict__ gx, const float* __restrict__ whh_t, const float* __restrict__ h0,
            const float* __restrict__ c0, float* __restrict__ hs, float* __restrict__ hT,
-           float* __restrict__ cT, int T, int H) {
+           float* __restrict__ cT, int T, int H, int n_seq) {
     extern __shared__ float sm[];
+    {   // sequence blockIdx.x of n_seq: gx [T, n_seq, 4H], hs [T, n_seq, H], states [n_seq, H]
+        const int sq = blockIdx.x;
+        gx += (long long)sq * 4 * H;
+        hs += (long long)sq * H;
+        if (h0) h0 += (long long)sq * H;
+        if (c0) c0 += (long long)sq * H;
+        if (hT) hT += (long long)sq * H;
+        if (cT) cT += (long long)sq * H;
+    }
+    const long long gstep = (long long)n_seq * 4 * H, hstep = (long long)n_seq * H;
     float* s_h = sm;            // [H]
     float* s_c = sm + H;        // [H]
     float* s_g = sm + 2 * H;    // [4H]
@@ -401,7 +411,7 @@ k_lstm_seq(const float* __restrict__ gx, const float* __restrict__ whh_t, const 
     __syncthreads();
     for (int t = 0; t < T; ++t) {
         for (int r = threadIdx.x; r < G; r += blockDim.x) {
-            float acc = gx[(long long)t * G + r];
+            float acc = gx[(long long)t * gstep + r];
             const float* wp = whh_t + r;
 #pragma unroll 4
             for (int j = 0; j < H; ++j) acc = fmaf(s_h[j], __ldg(wp + (long long)j * G), acc);
@@ -417,7 +427,7 @@ k_lstm_seq(const float* __restrict__ gx, const float* __restrict__ whh_t, const 
             const float h = og * tanhf(c);
             s_c[j] = c;
             s_h[j] = h;
-            hs[(long long)t * H + j] = h;
+            hs[(long long)t * hstep + j] = h;
         }
         __syncthreads();
     }
@@ -581,11 +591,11 @@ extern "C" int evfly_form_input_f32(float* d_x, float* d_out, int64_t n, int64_t
 
 extern "C" int evfly_lstm_seq_f32(const float* d_gx, const float* d_whh_t, const float* d_h0,
                                   const float* d_c0, float* d_hs, float* d_hT, float* d_cT, int T, int H,
-                                  void* stream) {
-    EVFLY_REQUIRE(d_gx && d_whh_t && d_hs && T >= 0 && H > 0 && H <= 2048, "lstm_seq_f32: bad argument");
+                                  int n_seq, void* stream) {
+    EVFLY_REQUIRE(d_gx && d_whh_t && d_hs && T >= 0 && H > 0 && H <= 2048 && n_seq > 0, "lstm_seq_f32: bad argument");
     const size_t smem = (size_t)6 * H * sizeof(float);
     const int threads = 4 * H >= 1024 ? 1024 : ((4 * H + 31) / 32) * 32;
-    k_lstm_seq<<<1, threads, smem, (cudaStream_t)stream>>>(d_gx, d_whh_t, d_h0, d_c0, d_hs, d_hT, d_cT, T, H);
+    k_lstm_seq<<<n_seq, threads, smem, (cudaStream_t)stream>>>(d_gx, d_whh_t, d_h0, d_c0, d_hs, d_hT, d_cT, T, H, n_seq);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

@@ -241,9 +241,18 @@ k_dwconv3x3_gelu(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 __global__ void __launch_bounds__(1024)
 k_lstm_seq_smemw(const float* __restrict__ gx, const __nv_bfloat162* __restrict__ whh_pairs, const float* __restrict__ h0,
                  const float* __restrict__ c0, float* __restrict__ hs, float* __restrict__ hT, float* __restrict__ cT, int T,
-                 int H) {
+                 int H, int n_seq) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int G = 4 * H;
+    // sequence blockIdx.x of n_seq: gx [T, n_seq, 4H], hs [T, n_seq, H], states [n_seq, H] (time-major batch)
+    const int sq = blockIdx.x;
+    gx += (long long)sq * G;
+    hs += (long long)sq * H;
+    if (h0) h0 += (long long)sq * H;
+    if (c0) c0 += (long long)sq * H;
+    if (hT) hT += (long long)sq * H;
+    if (cT) cT += (long long)sq * H;
+    const long long gstep = (long long)n_seq * G, hstep = (long long)n_seq * H;
     __nv_bfloat162* s_w = reinterpret_cast<__nv_bfloat162*>(sm_raw);        // [H/2][G]
     float* s_h = reinterpret_cast<float*>(sm_raw + (size_t)(H / 2) * G * 4);  // [H]
     float* s_c = s_h + H;                                                     // [H]
@@ -259,7 +268,7 @@ k_lstm_seq_smemw(const float* __restrict__ gx, const __nv_bfloat162* __restrict_
     for (int t = 0; t < T; ++t) {
         if (r < G) {
             float acc0 = gx_next, acc1 = 0.f;
-            if (t + 1 < T) gx_next = gx[(long long)(t + 1) * G + r];   // hide the L2 latency behind this step's dot product
+            if (t + 1 < T) gx_next = gx[(long long)(t + 1) * gstep + r];   // hide the L2 latency behind this step's dot product
 #pragma unroll 8
             for (int j2 = 0; j2 < H / 2; ++j2) {
                 const float2 wv = __bfloat1622float2(s_w[j2 * G + r]);
@@ -279,7 +288,7 @@ k_lstm_seq_smemw(const float* __restrict__ gx, const __nv_bfloat162* __restrict_
             const float h = og * tanhf(c);
             s_c[r] = c;
             s_h[r] = h;
-            hs[(long long)t * H + r] = h;
+            hs[(long long)t * hstep + r] = h;
         }
         __syncthreads();
     }
@@ -353,8 +362,8 @@ extern "C" int evfly_dwconv3x3_gelu_nhwc_bf16(const void* d_x, const float* d_w,
 }
 
 extern "C" int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float* d_h0, const float* d_c0, float* d_hs,
-                                    float* d_hT, float* d_cT, int T, int H, void* stream) {
-    EVFLY_REQUIRE(d_gx && d_whh_pairs && d_hs && T >= 0 && H > 0 && H % 2 == 0 && 4 * H <= 1024, "lstm_seq_smemw: bad argument (H even, 4H <= 1024)");
+                                    float* d_hT, float* d_cT, int T, int H, int n_seq, void* stream) {
+    EVFLY_REQUIRE(d_gx && d_whh_pairs && d_hs && T >= 0 && H > 0 && H % 2 == 0 && 4 * H <= 1024 && n_seq > 0, "lstm_seq_smemw: bad argument (H even, 4H <= 1024)");
     const size_t smem = (size_t)(H / 2) * 4 * H * 4 + (size_t)6 * H * 4;
     EVFLY_REQUIRE(smem <= 220 * 1024, "lstm_seq_smemw: W_hh does not fit shared memory (H=%d)", H);
     static bool attr = false;
@@ -363,8 +372,8 @@ extern "C" int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, 
         attr = true;
     }
     const int threads = ((4 * H + 31) / 32) * 32;
-    k_lstm_seq_smemw<<<1, threads, smem, (cudaStream_t)stream>>>(d_gx, reinterpret_cast<const __nv_bfloat162*>(d_whh_pairs), d_h0, d_c0,
-                                                                 d_hs, d_hT, d_cT, T, H);
+    k_lstm_seq_smemw<<<n_seq, threads, smem, (cudaStream_t)stream>>>(d_gx, reinterpret_cast<const __nv_bfloat162*>(d_whh_pairs), d_h0, d_c0,
+                                                                     d_hs, d_hT, d_cT, T, H, n_seq);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

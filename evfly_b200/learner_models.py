@@ -317,7 +317,7 @@ class OrigUNet(PackedModule):
         return ops.conv2d(x, m.weight, m.bias, act=act, **kw)
 
     # ---- exact path: CUDA-core fp32 kernels --------------------------------------------------------
-    def _unet_fp32(self, im, state, pk):
+    def _unet_fp32(self, im, state, pk, n_traj=1):
         N, dev = im.shape[0], im.device
         # encoder: (3x3 valid conv + ReLU) x 2 per level, 2x2 max-pool between levels
         y_e1 = self._c("unet_e12", self._c("unet_e11", im))
@@ -328,8 +328,14 @@ class OrigUNet(PackedModule):
 
         h_unet = None
         if self.num_recurrent[0] > 0:
-            y_e5_lstm, h_unet = self.lstm(y_e5.unsqueeze(0), state)
-            y_e5 = y_e5_lstm[0].squeeze(0)
+            if n_traj == 1:
+                y_e5_lstm, h_unet = self.lstm(y_e5.unsqueeze(0), state)
+                y_e5 = y_e5_lstm[0].squeeze(0)
+            else:   # time-major batch of trajectories [T*n, C, h, w] -> [n, T, C, h, w] for the (batch_first) ConvLSTM
+                T = N // n_traj
+                seq = y_e5.view(T, n_traj, *y_e5.shape[1:]).transpose(0, 1)
+                y_e5_lstm, h_unet = self.lstm(seq, state)
+                y_e5 = y_e5_lstm[0].transpose(0, 1).reshape(N, *y_e5.shape[1:])
 
         y_upconv = None
         y_interp = None
@@ -353,7 +359,7 @@ class OrigUNet(PackedModule):
         return (lambda: y_e5), h_unet, y_upconv, y_interp
 
     # ---- fast path: bf16 NHWC pitch grids on the tensor cores -----------------------------------
-    def _unet_bf16(self, im, state, W):
+    def _unet_bf16(self, im, state, W, n_traj=1):
         N, dev = im.shape[0], im.device
         b = lambda name: getattr(self, "unet_" + name).bias
         cv = lambda g, name: tc.conv3x3(g, W[name], b(name), relu=True)
@@ -365,7 +371,7 @@ class OrigUNet(PackedModule):
 
         h_unet = None
         if self.num_recurrent[0] > 0:
-            y_e5, h_unet = self._convlstm_bf16(y_e5, state, W["lstm"])
+            y_e5, h_unet = self._convlstm_bf16(y_e5, state, W["lstm"], n_traj)
 
         y_upconv = None
         y_interp = None
@@ -397,13 +403,15 @@ class OrigUNet(PackedModule):
             y_interp = ops.resize_bilinear(y_upconv, (self.input_h, self.input_w), align_corners=False)
         return (lambda: tc.grid_to_nchw(y_e5.data, y_e5.vh, y_e5.vw)), h_unet, y_upconv, y_interp
 
-    def _convlstm_bf16(self, g, state, Wl):
-        """ConvLSTM (1x1 kernel, no bias) over the N = time axis on the pitch grid: the x half of the
-        gate conv is ONE tensor-core GEMM over all steps; the h half is one small GEMM per step whose
-        epilogue adds the x gates and performs the cell update (fp32 c, bf16 h), all T steps enqueued
-        by one C-ABI call."""
-        T, Hp, Wp, dev = g.N, g.Hp, g.Wp, g.data.device
-        P = Hp * Wp
+    def _convlstm_bf16(self, g, state, Wl, n_traj=1):
+        """ConvLSTM (1x1 kernel, no bias) over the time axis on the pitch grid: the x half of the gate conv is ONE
+        tensor-core GEMM over all steps; the h half is one small GEMM per step whose epilogue adds the x gates and
+        performs the cell update (fp32 c, bf16 h), all T steps enqueued by one C-ABI call.
+        g holds T*n_traj frames in time-major order (frame t*n_traj + s): the n_traj trajectories advance together,
+        so a step's GEMM has n_traj * Hp*Wp rows. States are [n_traj, Ch, vh, vw] (n_traj = 1: the reference's)."""
+        Hp, Wp, dev = g.Hp, g.Wp, g.data.device
+        T = g.N // n_traj
+        P = n_traj * Hp * Wp            # rows advanced per step
         states = []
         cur = g
         for li, (wx, wh) in enumerate(Wl):
@@ -413,22 +421,27 @@ class OrigUNet(PackedModule):
             c = torch.zeros((P, Ch), dtype=torch.float32, device=dev)
             h_all = torch.empty((T + 1, P, Ch), dtype=tc.BF16, device=dev)      # block 0 = h_0, block t+1 = h_t
             if state is not None:
-                hs, cs = to_dev(state[li][0], dev), to_dev(state[li][1], dev)        # [1,Ch,vh,vw] each
+                hs, cs = to_dev(state[li][0], dev), to_dev(state[li][1], dev)        # [n_traj,Ch,vh,vw] each
                 h_all[0].copy_(tc.nchw_to_grid(hs, Hp, Wp).data.view(P, Ch))
-                ops.map4d(cs[0].permute(1, 2, 0), c.view(Hp, Wp, Ch)[:g.vh, :g.vw])
+                ops.map4d(cs.permute(0, 2, 3, 1), c.view(n_traj, Hp, Wp, Ch)[:, :g.vh, :g.vw])
             else:
                 h_all[0].zero_()
             tc.convlstm_scan(h_all, wh, gx, c, T, P, Ch)     # T fused step kernels enqueued from C++
-            out = tc.Grid(h_all[1:].view(T, Hp, Wp, Ch), g.vh, g.vw)
-            hview = out.data.view(T, P, Ch)
-            h_last = tc.grid_to_nchw(hview[T - 1].view(1, Hp, Wp, Ch), g.vh, g.vw)
-            c_last = torch.empty((1, Ch, g.vh, g.vw), dtype=torch.float32, device=dev)
-            ops.map4d(c.view(Hp, Wp, Ch)[:g.vh, :g.vw].permute(2, 0, 1), c_last[0])
+            out = tc.Grid(h_all[1:].view(T * n_traj, Hp, Wp, Ch), g.vh, g.vw)
+            h_last = tc.grid_to_nchw(h_all[T].view(n_traj, Hp, Wp, Ch), g.vh, g.vw)
+            c_last = torch.empty((n_traj, Ch, g.vh, g.vw), dtype=torch.float32, device=dev)
+            ops.map4d(c.view(n_traj, Hp, Wp, Ch)[:, :g.vh, :g.vw].permute(0, 3, 1, 2), c_last)
             states.append([h_last, c_last])
             cur = out
         return cur, states[-1:]
 
-    def forward(self, x):
+    def forward_trajectories(self, x, n_traj):
+        """Extension for config 4: n_traj independent trajectories of equal length advance together.
+        x[0] holds T*n_traj frames in TIME-MAJOR order (frame t*n_traj + s belongs to trajectory s); recurrent states
+        carry a leading n_traj dimension ([n_traj,512,8,13] for the ConvLSTM). Same outputs as forward()."""
+        return self.forward(x, n_traj=n_traj)
+
+    def forward(self, x, n_traj=1):
         """x = [frames [N,1,H,W], desvel (unused), [h_unet, h_velpred] or None]
         -> (vel [N,3], (y_interp, y_upconv, (h_unet, h_velpred)))   (learner_models.py:521-616)"""
         self._check_inference()
@@ -442,9 +455,9 @@ class OrigUNet(PackedModule):
             x[2] = (None, None)
 
         if self.precision == 'bf16':
-            y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_bf16(im, x[2][0], pk["bf16"])
+            y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_bf16(im, x[2][0], pk["bf16"], n_traj)
         else:
-            y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_fp32(im, x[2][0], pk)
+            y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_fp32(im, x[2][0], pk, n_traj)
 
         y_vel = torch.zeros((N, 3), dtype=torch.float32, device=dev)   # default [1,0,0]: forward, full speed
         y_vel[:, 0] = 1.0
@@ -456,7 +469,7 @@ class OrigUNet(PackedModule):
             feat = self.convnet_velpred(src)
             feat = feat.reshape(N, -1)
             if self.num_recurrent[1] > 0:
-                feat, h_velpred = run_lstm(ops, pk["lstm_velpred"], feat, x[2][1], self.lstm_velpred.hidden_size)
+                feat, h_velpred = run_lstm(ops, pk["lstm_velpred"], feat, x[2][1], self.lstm_velpred.hidden_size, n_seq=n_traj)
             y_vel, _ = self.velpred_head([feat])
         return y_vel, (y_interp, y_upconv, (h_unet, h_velpred))
 
@@ -470,12 +483,17 @@ class OrigUNet_w_VITFLY_ViTLSTM(nn.Module):
         self.vitfly_vitlstm = vitfly_models.LSTMNetVIT()
         print(f'[OrigUNet_w_VITFLY_ViTLSTM] Number of parameters: {sum(p.numel() for p in self.parameters()):,}')
 
-    def forward(self, X):
+    def forward_trajectories(self, X, n_traj):
+        """Extension for config 4: n_traj trajectories advance together; frames / desvel are time-major
+        (row t*n_traj + s), ConvLSTM states [n_traj,512,8,13], LSTM states [3,n_traj,128]."""
+        return self.forward(X, n_traj=n_traj)
+
+    def forward(self, X, n_traj=1):
         """X = [frames, desvel, [h_unet, None] or None, (h,c) or None]
         -> (vel, (depth, y_upconv, ((h_unet, h_velpred), (h,c))))   (learner_models.py:629-636)"""
         x = X[0]
-        _, (x_depth, y_upconv, (h_unet, h_velpred)) = self.origunet([x, None, X[2]])
+        _, (x_depth, y_upconv, (h_unet, h_velpred)) = self.origunet.forward([x, None, X[2]], n_traj=n_traj)
         # * 2 roughly matches the depth scale VITFLY_ViTLSTM was trained on (:634)
         x_depth_input = ops.map4d(x_depth, mul=2.0, lo=0.0, hi=1.0)
-        x_vel, h_vitlstm = self.vitfly_vitlstm([x_depth_input, X[1], None, X[3]])
+        x_vel, h_vitlstm = self.vitfly_vitlstm.forward([x_depth_input, X[1], None, X[3]], n_traj=n_traj)
         return x_vel, (x_depth, y_upconv, ((h_unet, h_velpred), h_vitlstm))

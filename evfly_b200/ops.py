@@ -172,7 +172,7 @@ def lstm_layer_seq(gx, whh_t, h0, c0):
     hT = torch.empty((H,), dtype=torch.float32, device=gx.device)
     cT = torch.empty((H,), dtype=torch.float32, device=gx.device)
     _lib.check(lib.evfly_lstm_seq_f32(_lib.ptr(gx), _lib.ptr(whh_t), _lib.ptr(h0), _lib.ptr(c0), _lib.ptr(hs), _lib.ptr(hT),
-                                      _lib.ptr(cT), T, H, _lib.stream_ptr()), "evfly_lstm_seq_f32")
+                                      _lib.ptr(cT), T, H, 1, _lib.stream_ptr()), "evfly_lstm_seq_f32")
     return hs, hT, cT
 
 

@@ -56,6 +56,22 @@ class PerceptionPipeline:
             self.state_unet, self.state_vit = hu, hv
         return vel, depth
 
+    def run_trajectories(self, records_list, edges_list, want_voxel=True):
+        """Config 4: several independent trajectories of equal length T on one GPU. Each trajectory is accumulated
+        on its own (its events are its own stream); the model then advances all of them together, frames in
+        time-major order, so the recurrent scans run n_traj-wide. Fresh state. Returns (vel [n_traj,T,3], depth
+        [n_traj,T,1,h,w])."""
+        n = len(records_list)
+        frames = []
+        for rec, edges in zip(records_list, edges_list):
+            f, _, _ = self.frames_from_windows(rec, edges, want_voxel)
+            frames.append(f)
+        T = frames[0].shape[0]
+        tm = torch.stack(frames, dim=1).reshape(T * n, 1, self.h, self.w)        # frame t*n + s
+        desvel = torch.full((T * n, 1), self.desvel, dtype=torch.float32, device=self.dev)
+        vel, (depth, _, _) = self.model.forward_trajectories([tm, desvel, [None, None], None], n)
+        return vel.view(T, n, 3).transpose(0, 1), depth.view(T, n, 1, self.h, self.w).transpose(0, 1)
+
     def __call__(self, records, edges_ns, want_voxel=True):
         frames, counts, voxel = self.frames_from_windows(records, edges_ns, want_voxel)
         vel, depth = self.forward(frames)
@@ -63,14 +79,16 @@ class PerceptionPipeline:
 
 
 class TrajectoryFeeder:
-    """End-to-end path for offline evaluation (learner/evaluation_tools.py:62-66 feeds trajectories one
-    after another from host memory): host batches of packed event records are staged through two device
-    buffers on a copy stream, so the H2D copy of trajectory i+1 overlaps the compute of trajectory i.
+    """End-to-end path for offline evaluation (learner/evaluation_tools.py:62-66 feeds trajectories one after
+    another from host memory): host batches of packed event records are staged through two device buffers on a
+    copy stream, so the H2D copy of batch i+1 overlaps the compute of batch i.
 
-        feeder = TrajectoryFeeder(pipe, max_events)
-        for vel in feeder.run(batches):   # batches: iterable of (pinned uint8 [n,16], edges_ns int64 device [T+1])
-            ...                           # vel: pinned host tensor [T,3], valid until the next iteration
-    """
+        feeder = TrajectoryFeeder(pipe, max_events, max_windows)
+        for vel in feeder.run(batches):
+            ...        # vel: pinned host tensor [n_traj, T, 3], valid until the next iteration
+    A batch is (records, edges) for one trajectory or ([records...], [edges...]) for several trajectories of equal
+    length that advance together (PerceptionPipeline.run_trajectories); records are pinned uint8 [n,16] host
+    tensors, edges int64 device tensors [T+1]."""
 
     def __init__(self, pipe: "PerceptionPipeline", max_events: int, max_windows: int):
         dev = pipe.dev
@@ -82,11 +100,18 @@ class TrajectoryFeeder:
         self.h_vel = [torch.empty((max_windows, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
 
-    def _stage(self, slot, records):
-        main = torch.cuda.current_stream()
+    @staticmethod
+    def _as_lists(batch):
+        recs, edges = batch
+        return (list(recs), list(edges)) if isinstance(recs, (list, tuple)) else ([recs], [edges])
+
+    def _stage(self, slot, recs):
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.free[slot])
-            self.bufs[slot][: records.shape[0]].copy_(records, non_blocking=True)
+            off = 0
+            for r in recs:
+                self.bufs[slot][off: off + r.shape[0]].copy_(r, non_blocking=True)
+                off += r.shape[0]
             self.ready[slot].record(self.copy_stream)
 
     def run(self, batches):
@@ -97,22 +122,31 @@ class TrajectoryFeeder:
         cur = next(it, None)
         if cur is None:
             return
-        self._stage(0, cur[0])
+        self._stage(0, self._as_lists(cur)[0])
         slot = 0
         while cur is not None:
             nxt = next(it, None)
             if nxt is not None:
-                self._stage(slot ^ 1, nxt[0])          # overlaps with the compute below
+                self._stage(slot ^ 1, self._as_lists(nxt)[0])          # overlaps with the compute below
             main.wait_event(self.ready[slot])
-            n, T = cur[0].shape[0], cur[1].shape[0] - 1
+            recs, edges = self._as_lists(cur)
+            views, off = [], 0
+            for r in recs:
+                views.append(self.bufs[slot][off: off + r.shape[0]])
+                off += r.shape[0]
+            n, T = len(recs), edges[0].shape[0] - 1
             with torch.no_grad():
                 self.pipe.reset()
-                vel, _, _, _ = self.pipe(self.bufs[slot][:n], cur[1])
-                self.h_vel[slot][:T].copy_(vel, non_blocking=True)
+                if n == 1:
+                    vel = self.pipe(views[0], edges[0])[0].view(1, T, 3)
+                else:
+                    vel = self.pipe.run_trajectories(views, edges)[0]
+                out = self.h_vel[slot][: n * T].view(n, T, 3)
+                out.copy_(vel, non_blocking=True)
             self.free[slot].record(main)
             self.done[slot].record(main)
             self.done[slot].synchronize()
-            yield self.h_vel[slot][:T]
+            yield out
             cur, slot = nxt, slot ^ 1
 
 

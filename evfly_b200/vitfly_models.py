@@ -103,7 +103,11 @@ class LSTMNetVIT(_ViTEncoder):
         dec = sn_effective_weight(self.decoder)
         return {"decoder": dec, "decoder_bf16": dec.to(tc.BF16).contiguous(), "fc2": sn_effective_weight(self.nn_fc2), "lstm": pack_lstm(self.lstm)}
 
-    def forward(self, X):
+    def forward_trajectories(self, X, n_traj):
+        """Extension: n_traj sequences advance together (rows time-major, state [3, n_traj, 128])."""
+        return self.forward(X, n_traj=n_traj)
+
+    def forward(self, X, n_traj=1):
         X = _inputs(self, X)
         pk = self.packed()
         N = X[0].shape[0]
@@ -114,7 +118,7 @@ class LSTMNetVIT(_ViTEncoder):
         else:
             ops.linear(feat, pk["decoder"], self.decoder.bias, out2d=feat_out)
         state = X[3] if len(X) > 3 else None
-        out, h = run_lstm(ops, pk["lstm"], seq, state, 128, smem_weights=self.precision == 'bf16')
+        out, h = run_lstm(ops, pk["lstm"], seq, state, 128, smem_weights=self.precision == 'bf16', n_seq=n_traj)
         out = ops.linear(out, pk["fc2"], self.nn_fc2.bias)
         return out, h
 

@@ -291,9 +291,11 @@ int evfly_form_input_f32(float* d_x, float* d_out, int64_t n, int64_t plane, int
 /* nn.LSTM over an UNBATCHED sequence (the reference feeds [N,feat], so N is time): one layer.
  * d_gx [T,4H] = x_t W_ih^T + b_ih + b_hh (a conv2d_f32 call), gate order i,f,g,o;
  * d_whh_t [H,4H] = W_hh transposed; d_h0/d_c0 [H] (NULL = zeros); d_hs [T,H] receives every h_t;
- * d_hT/d_cT [H] the final state. One persistent CTA walks the T steps with h,c in shared memory. */
+ * d_hT/d_cT [H] the final state. One persistent CTA walks the T steps with h,c in shared memory.
+ * n_seq > 1 runs that many independent sequences (trajectories of one rank), one CTA each, on
+ * time-major batches: d_gx [T, n_seq, 4H], d_hs [T, n_seq, H], states [n_seq, H].               */
 int evfly_lstm_seq_f32(const float* d_gx, const float* d_whh_t, const float* d_h0, const float* d_c0,
-                       float* d_hs, float* d_hT, float* d_cT, int T, int H, void* stream);
+                       float* d_hs, float* d_hT, float* d_cT, int T, int H, int n_seq, void* stream);
 
 /* ConvLSTM cell pointwise (convlstm.py:44-53), gate order i,f,o,g: gates [4*Ch, P],
  * c [Ch,P] updated in place, h_out [Ch,P]:  c = sig(f)*c + sig(i)*tanh(g);  h = sig(o)*tanh(c).  */
@@ -408,7 +410,7 @@ int evfly_dwconv3x3_gelu_nhwc_bf16(const void* d_x, const float* d_w, const floa
 /* evfly_lstm_seq_f32 with W_hh resident in shared memory as bf16: d_whh_pairs is bf16x2
  * [H/2][4H] = {W_hh[r][2j], W_hh[r][2j+1]} at [j][r]; state and gates stay fp32. 4H <= 1024.       */
 int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float* d_h0, const float* d_c0,
-                         float* d_hs, float* d_hT, float* d_cT, int T, int H, void* stream);
+                         float* d_hs, float* d_hT, float* d_cT, int T, int H, int n_seq, void* stream);
 
 /* 3x3 valid conv + bias (+ReLU) for Cin, Cout in {32, 64} with the input halo reused from shared memory
  * (one 4-D TMA box [18 x 10 pixels] per 16x8 output tile, all 9 taps read through shifted UMMA

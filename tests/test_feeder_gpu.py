@@ -25,8 +25,12 @@ def test_feeder_matches_pipeline(cuda_lib):
             batches.append((pinned, d_edges))
             pipe.reset()
             want.append(pipe(pinned.cuda(), d_edges)[0].cpu())
-        feeder = TrajectoryFeeder(pipe, max_events=4 * 50_000, max_windows=4)
+        feeder = TrajectoryFeeder(pipe, max_events=6 * 50_000, max_windows=6)
         got = [v.clone() for v in feeder.run(batches)]
         assert len(got) == 4
         for g, w in zip(got, want):
-            assert torch.equal(g, w)          # same kernels, same inputs: bit-identical
+            assert torch.equal(g[0], w)          # same kernels, same inputs: bit-identical
+        # multi-trajectory batches advance together
+        multi = [([batches[0][0], batches[0][0]], [batches[0][1], batches[0][1]])]
+        (v,) = [v.clone() for v in feeder.run(multi)]
+        assert v.shape == (2, 3, 3) and torch.allclose(v[0], want[0], rtol=2e-2, atol=2e-3) and torch.equal(v[0], v[1])
