@@ -70,6 +70,7 @@ SIGNATURES.update({
     "evfly_pixel_shuffle_f32": (_i32, [_vp, _p64, _vp, _p64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_form_input_f32": (_i32, [_vp, _vp, _i64, _i64, _i32, _f32, _vp]),
     "evfly_lstm_seq_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "evfly_lstm_pointwise_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "evfly_convlstm_pointwise_f32": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "evfly_velpred_unit_f32": (_i32, [_vp, _vp, _i32, _vp]),
 })

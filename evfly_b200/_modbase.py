@@ -72,7 +72,7 @@ def bn_affine(bn: nn.BatchNorm2d):
 
 
 def pack_lstm(lstm: nn.LSTM):
-    """Per layer: (W_ih [4H,in], b_ih+b_hh or None, W_hh^T [H,4H])."""
+    """Per layer: (W_ih [4H,in], b_ih+b_hh or None, W_hh^T [H,4H], bf16 W_hh pairs or None, W_hh [4H,H])."""
     layers = []
     for l in range(lstm.num_layers):
         w_ih = getattr(lstm, f"weight_ih_l{l}").contiguous()
@@ -85,7 +85,7 @@ def pack_lstm(lstm: nn.LSTM):
         if H % 2 == 0 and 4 * H <= 1024 and (H // 2) * 4 * H * 4 + 24 * H <= 220 * 1024:
             from . import tc
             pairs = tc.pack_lstm_whh_pairs(getattr(lstm, f"weight_hh_l{l}"))
-        layers.append((w_ih, b, w_hh_t, pairs))
+        layers.append((w_ih, b, w_hh_t, pairs, getattr(lstm, f"weight_hh_l{l}").contiguous()))
     return layers
 
 
@@ -105,7 +105,29 @@ def run_lstm(ops, packed_layers, seq, state, hidden, smem_weights=False, n_seq=1
         assert tuple(h0.shape) == st_shape and tuple(c0.shape) == st_shape, "LSTM state shape"
     lib = _lib.load()
     inp = seq
-    for l, (w_ih, b, w_hh_t, pairs) in enumerate(packed_layers):
+    T_all = seq.shape[0] // n_seq
+    if T_all <= 4 and n_seq <= 8:
+        # short sequences (batch-1 streaming): a persistent single-CTA scan would stream W_hh through one SM;
+        # instead each step's gate GEMV runs on the multi-CTA small-M Linear, then one pointwise kernel
+        for l, (w_ih, b, w_hh_t, pairs, w_hh) in enumerate(packed_layers):
+            gx = ops.linear(inp, w_ih, b)                                   # [T*n_seq, 4H]
+            hs = torch.empty((T_all * n_seq, hidden), dtype=torch.float32, device=dev)
+            h_prev = None if h0 is None else h0[l].reshape(n_seq, hidden)
+            c_prev = None if c0 is None else c0[l].reshape(n_seq, hidden)
+            for t in range(T_all):
+                g_t = gx[t * n_seq:(t + 1) * n_seq]
+                if h_prev is not None:
+                    g_t = ops.linear(h_prev, w_hh, None, res2d=g_t)
+                last = t == T_all - 1
+                h_t = hs[t * n_seq:(t + 1) * n_seq]
+                c_t = c_out[l].reshape(n_seq, hidden) if last else torch.empty((n_seq, hidden), dtype=torch.float32, device=dev)
+                _lib.check(lib.evfly_lstm_pointwise_f32(g_t.data_ptr(), None if c_prev is None else c_prev.data_ptr(), c_t.data_ptr(),
+                                                        h_t.data_ptr(), h_out[l].data_ptr() if last else None, n_seq, hidden,
+                                                        _lib.stream_ptr()), "evfly_lstm_pointwise_f32")
+                h_prev, c_prev = h_t, c_t
+            inp = hs
+        return inp, (h_out, c_out)
+    for l, (w_ih, b, w_hh_t, pairs, _w_hh) in enumerate(packed_layers):
         gx = ops.linear(inp, w_ih, b)
         T = gx.shape[0] // n_seq
         hs = torch.empty((T * n_seq, hidden), dtype=torch.float32, device=dev)

@@ -141,6 +141,44 @@ k_conv2d_f32(const evfly_conv2d_args a, const int OH, const int OW, const long l
 }
 
 // ---------------------------------------------------------------------------------------
+// Tiny convolutions (batch-1: the 48->12 down_sample conv, heads): the 64x64-tile kernel would run on a
+// handful of CTAs with a long serial K loop; here every output element gets its own thread.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_conv2d_small(const evfly_conv2d_args a, const int OH, const int OW, const long long M, const int K, const int cin_g, const int cout_g) {
+    // one WARP per output element; the lanes split K and reduce by shuffle
+    const long long idx = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (idx >= M * a.Cout) return;
+    const int lane = threadIdx.x & 31;
+    const long long m = idx % M;
+    const int c = (int)(idx / M);
+    const int g = c / cout_g;
+    const int ow = (int)(m % OW), oh = (int)((m / OW) % OH);
+    const long long n = m / ((long long)OW * OH);
+    const int ih0 = oh * a.stride - a.pad, iw0 = ow * a.stride - a.pad;
+    const float* __restrict__ wp = a.w + (long long)c * K;
+    const float* __restrict__ xp = a.x + n * a.xs[0] + (long long)(g * cin_g) * a.xs[1];
+    const int KHW = a.KH * a.KW;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const int ci = k / KHW, r = k - ci * KHW;
+        const int kh = r / a.KW, kw = r - kh * a.KW;
+        const int ih = ih0 + kh, iw = iw0 + kw;
+        if ((unsigned)ih < (unsigned)a.H && (unsigned)iw < (unsigned)a.W)
+            acc = fmaf(__ldg(xp + ci * a.xs[1] + ih * a.xs[2] + iw * a.xs[3]), __ldg(wp + k), acc);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane != 0) return;
+    if (a.bias) acc += a.bias[c];
+    acc = apply_act(acc, a.act);
+    if (a.post_scale) acc = acc * a.post_scale[c] + a.post_shift[c];
+    const long long o = n * a.ys[0] + (long long)c * a.ys[1] + (long long)oh * a.ys[2] + (long long)ow * a.ys[3];
+    if (a.res) acc += a.res[o];
+    a.y[o] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
 // Linear with a handful of rows (batch-1 streaming: the 4608->512 decoder, the LSTM input
 // projection, the heads): weight-bandwidth bound, so one warp per output feature streams its
 // weight row once (coalesced) and serves all M <= 8 input rows from shared memory.
@@ -437,6 +475,24 @@ k_lstm_seq(const float* __restrict__ gx, const float* __restrict__ whh_t, const 
     }
 }
 
+// LSTM cell update for a few rows (short sequences / batch-1 streaming): gates [n, 4H] (i,f,g,o),
+// c [n,H] in -> out, h [n,H] out. The gate GEMV runs on k_linear_smallm across many CTAs.
+__global__ void __launch_bounds__(256)
+k_lstm_pointwise(const float* __restrict__ gates, const float* __restrict__ c_in, float* __restrict__ c_out,
+                 float* __restrict__ h_out, float* __restrict__ h_out2, int n, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * H) return;
+    const int r = i / H, j = i - r * H;
+    const float* g = gates + (long long)r * 4 * H;
+    const float ig = 1.f / (1.f + expf(-g[j])), fg = 1.f / (1.f + expf(-g[H + j]));
+    const float gg = tanhf(g[2 * H + j]), og = 1.f / (1.f + expf(-g[3 * H + j]));
+    const float c = fg * (c_in ? c_in[i] : 0.f) + ig * gg;
+    const float h = og * tanhf(c);
+    c_out[i] = c;
+    h_out[i] = h;
+    if (h_out2) h_out2[i] = h;
+}
+
 __global__ void __launch_bounds__(256)
 k_convlstm_pointwise(const float* __restrict__ gates, float* __restrict__ c, float* __restrict__ h,
                      int Ch, int P) {
@@ -482,6 +538,11 @@ extern "C" int evfly_conv2d_f32(const evfly_conv2d_args* p, void* stream) {
     const long long M = (long long)a.N * OH * OW;
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
     const int K = cin_g * a.KH * a.KW;
+    if (M * a.Cout <= 32768 && K <= 2048 && ceil_div(M, CBM) * ceil_div(cout_g, CBN) * a.groups < 64) {
+        k_conv2d_small<<<(unsigned)ceil_div(M * a.Cout, 8), 256, 0, (cudaStream_t)stream>>>(a, OH, OW, M, K, cin_g, cout_g);
+        EVFLY_LAUNCHED();
+        return EVFLY_OK;
+    }
     const long long gx = ceil_div(M, CBM);
     EVFLY_REQUIRE(gx < (1ll << 31) && a.groups < 65536, "conv2d_f32: problem too large for one grid");
     dim3 grid((unsigned)gx, (unsigned)ceil_div(cout_g, CBN), (unsigned)a.groups);
@@ -596,6 +657,14 @@ extern "C" int evfly_lstm_seq_f32(const float* d_gx, const float* d_whh_t, const
     const size_t smem = (size_t)6 * H * sizeof(float);
     const int threads = 4 * H >= 1024 ? 1024 : ((4 * H + 31) / 32) * 32;
     k_lstm_seq<<<n_seq, threads, smem, (cudaStream_t)stream>>>(d_gx, d_whh_t, d_h0, d_c0, d_hs, d_hT, d_cT, T, H, n_seq);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_lstm_pointwise_f32(const float* d_gates, const float* d_c_in, float* d_c_out, float* d_h_out, float* d_h_out2,
+                                        int n, int H, void* stream) {
+    EVFLY_REQUIRE(d_gates && d_c_out && d_h_out && n > 0 && H > 0, "lstm_pointwise_f32: bad argument");
+    k_lstm_pointwise<<<(n * H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_gates, d_c_in, d_c_out, d_h_out, d_h_out2, n, H);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

@@ -215,24 +215,48 @@ __device__ SelectResult radix_select(const float* x, int64_t n, unsigned long lo
         const unsigned nb = 1u << widths[pass];
         for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) s_hist[b] = 0;
         __syncthreads();
+        // Event frames are ~65 % zeros: every zero lands in bin 0 of every pass, which would serialise the
+        // shared-memory atomics on one bank, so bin 0 is counted in a register and added once per thread.
+        unsigned zero_bin = 0;
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
             const unsigned u = __float_as_uint(x[i]) & 0x7fffffffu;
-            if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> sh) & (nb - 1)], 1u);
-        }
-        __syncthreads();
-        // single thread walks the histogram (<= 2048 bins; negligible next to the passes)
-        if (threadIdx.x == 0) {
-            unsigned long long acc = below;
-            unsigned b = 0;
-            for (; b < nb; ++b) {
-                const unsigned long long c = s_hist[b];
-                if (acc + c > k) break;
-                acc += c;
+            if ((u & mask) == prefix) {
+                const unsigned key = (u >> sh) & (nb - 1);
+                if (key == 0) ++zero_bin; else atomicAdd(&s_hist[key], 1u);
             }
-            if (b >= nb) b = nb - 1;  // cannot happen for k < n
-            s_misc[0] = b;
-            s_misc[1] = acc;
-            s_misc[2] = acc + s_hist[b];
+        }
+        if (zero_bin) atomicAdd(&s_hist[0], zero_bin);
+        __syncthreads();
+        // parallel search of the bin that holds rank k: every thread owns nb/1024 consecutive bins, block-wide
+        // exclusive scan of the per-thread sums (warp shuffles + one warp over the 32 warp totals)
+        {
+            const unsigned per = nb / kSelThreads;            // 2 (11-bit pass) or 1
+            const unsigned b0 = threadIdx.x * per;
+            const unsigned c0 = s_hist[b0], c1 = per == 2 ? s_hist[b0 + 1] : 0u;
+            unsigned incl = c0 + c1;
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += y;
+            }
+            __shared__ unsigned s_wsum[32];
+            if (lane == 31) s_wsum[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                unsigned wv = s_wsum[lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned y = __shfl_up_sync(0xffffffffu, wv, d);
+                    if (lane >= d) wv += y;
+                }
+                s_wsum[lane] = wv;       // inclusive warp totals
+            }
+            __syncthreads();
+            const unsigned long long excl = below + (wid ? s_wsum[wid - 1] : 0u) + (incl - c0 - c1);
+            // k falls into one of this thread's bins?
+            if (k >= excl && k < excl + c0) { s_misc[0] = b0; s_misc[1] = excl; s_misc[2] = excl + c0; }
+            else if (per == 2 && k >= excl + c0 && k < excl + c0 + c1) { s_misc[0] = b0 + 1; s_misc[1] = excl + c0; s_misc[2] = excl + c0 + c1; }
         }
         __syncthreads();
         const unsigned b = (unsigned)s_misc[0];

@@ -6,6 +6,8 @@
 // scan with W_hh resident in shared memory.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace evfly {
 
@@ -114,6 +116,78 @@ k_patch_embed_ln_block(const __nv_bfloat16* __restrict__ x, const float* __restr
     }
 }
 
+// Few-token variant (batch-1 streaming: the reduction conv yields 2..6 tokens per frame with K up to 2048):
+// a CLUSTER of 8 CTAs per token splits K eight ways, partial sums are reduced through distributed shared
+// memory by the cluster's rank-0 CTA, which then applies bias + LayerNorm.
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256)
+k_patch_embed_ln_cluster(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                         int H, int W, int Cin, int Cout, int k, int s, int p, int OH, int OW, float eps) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float s_patch[512];      // this CTA's K slice (<= 512 values)
+    __shared__ float s_part[8 * 64];    // per-warp partial sums
+    __shared__ float s_cta[64];         // this CTA's partial, read by rank 0 through DSMEM
+    const int K = k * k * Cin;
+    const int rank = (int)cluster.block_rank();
+    const long long tok = blockIdx.x / 8;
+    const int ow = (int)(tok % OW), oh = (int)((tok / OW) % OH);
+    const long long b = tok / ((long long)OW * OH);
+    const int per_cta = (K + 7) / 8;
+    const int k0 = rank * per_cta, k1 = min(K, k0 + per_cta);
+    for (int i = k0 + threadIdx.x; i < k1; i += blockDim.x) {
+        const int ci = i % Cin, t = i / Cin;
+        const int ih = oh * s - p + t / k, iw = ow * s - p + t % k;
+        float v = 0.f;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) v = bf2f(x[((b * H + ih) * (long long)W + iw) * Cin + ci]);
+        s_patch[i - k0] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool two = Cout > 32;
+    float a0 = 0.f, a1 = 0.f;
+    const int per_warp = (k1 - k0 + 7) / 8;
+    const int kw0 = k0 + warp * per_warp, kw1 = min(k1, kw0 + per_warp);
+#pragma unroll 4
+    for (int i = kw0; i < kw1; ++i) {
+        const float v = s_patch[i - k0];
+        a0 = fmaf(v, __ldg(w + (long long)i * Cout + lane), a0);
+        if (two) a1 = fmaf(v, __ldg(w + (long long)i * Cout + lane + 32), a1);
+    }
+    s_part[warp * 64 + lane] = a0;
+    s_part[warp * 64 + 32 + lane] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += s_part[q * 64 + threadIdx.x];
+        s_cta[threadIdx.x] = t;
+    }
+    cluster.sync();
+    if (rank == 0 && warp == 0) {
+        a0 = bias[lane];
+        a1 = two ? bias[lane + 32] : 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float* remote = cluster.map_shared_rank(s_cta, r);
+            a0 += remote[lane];
+            a1 += remote[lane + 32];
+        }
+        float sum = a0 + a1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        const float mean = sum / (float)Cout;
+        const float d0 = a0 - mean, d1 = two ? a1 - mean : 0.f;
+        float var = d0 * d0 + d1 * d1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+        const float rstd = rsqrtf(var / (float)Cout + eps);
+        __nv_bfloat16* o = out + tok * Cout;
+        o[lane] = __float2bfloat16_rn(d0 * rstd * gamma[lane] + beta[lane]);
+        if (two) o[lane + 32] = __float2bfloat16_rn(d1 * rstd * gamma[lane + 32] + beta[lane + 32]);
+    }
+    cluster.sync();     // keep every CTA's shared memory alive until rank 0 has read it
+}
+
 // LayerNorm over C (32 or 64) of bf16 rows, one warp per row
 __global__ void __launch_bounds__(256)
 k_layernorm_bf16(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -136,44 +210,44 @@ k_layernorm_bf16(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
     if (two) y[row * C + lane + 32] = __float2bfloat16_rn(d1 * rstd * gamma[lane + 32] + beta[lane + 32]);
 }
 
-// softmax(q k^T / sqrt(d)) v with n_kv <= 8 keys; one thread per (token, head); d = C/heads = 32
-__global__ void __launch_bounds__(128)
+// softmax(q k^T / sqrt(d)) v with n_kv <= 8 keys; one WARP per (token, head), lane = channel of the head
+// (d = C/heads <= 32): coalesced 64-byte reads of q / k / v, dot products by warp shuffle.
+__global__ void __launch_bounds__(256)
 k_attention_small_bf16(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv, __nv_bfloat16* __restrict__ out,
                        long long B, int N, int C, int heads, int n_kv) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= B * N * heads) return;
+    const int lane = threadIdx.x & 31;
     const int h = (int)(i % heads);
     const long long bn = i / heads, b = bn / N;
     const int d = C / heads;
-    const __nv_bfloat16* qp = q + bn * C + h * d;
-    const __nv_bfloat16* kvb = kv + b * n_kv * 2 * C;
-    float qv[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) qv[j] = j < d ? bf2f(qp[j]) : 0.f;
+    const bool on = lane < d;
+    const float qv = on ? bf2f(q[bn * C + h * d + lane]) : 0.f;
+    const __nv_bfloat16* kvb = kv + b * n_kv * 2 * C + h * d + lane;
     const float inv = rsqrtf((float)d);
-    float sc[8];
+    float sc[8], vv[8];
     float mx = -INFINITY;
-    for (int s = 0; s < n_kv; ++s) {
-        const __nv_bfloat16* kp = kvb + (long long)s * 2 * C + h * d;
-        float dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < d) dot = fmaf(qv[j], bf2f(kp[j]), dot);
-        sc[s] = dot * inv;
-        mx = fmaxf(mx, sc[s]);
+    for (int s = 0; s < 8; ++s) {
+        if (s < n_kv) {
+            float dot = on ? qv * bf2f(kvb[(long long)s * 2 * C]) : 0.f;
+            vv[s] = on ? bf2f(kvb[(long long)s * 2 * C + C]) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            sc[s] = dot * inv;
+            mx = fmaxf(mx, sc[s]);
+        }
     }
-    float den = 0.f;
-    for (int s = 0; s < n_kv; ++s) {
-        sc[s] = __expf(sc[s] - mx);
-        den += sc[s];
+    float den = 0.f, acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        if (s < n_kv) {
+            const float e = __expf(sc[s] - mx);
+            den += e;
+            acc = fmaf(e, vv[s], acc);
+        }
     }
-    const float rden = 1.f / den;
-    __nv_bfloat16* op = out + bn * C + h * d;
-    for (int j = 0; j < d; ++j) {
-        float acc = 0.f;
-        for (int s = 0; s < n_kv; ++s) acc = fmaf(sc[s] * rden, bf2f(kvb[(long long)s * 2 * C + C + h * d + j]), acc);
-        op[j] = __float2bfloat16_rn(acc);
-    }
+    if (on) out[bn * C + h * d + lane] = __float2bfloat16_rn(acc / den);
 }
 
 // MixFFN "depthwise" conv: groups = C, 8 -> 8 channels per group, 3x3, pad 1, + bias + exact GELU.
@@ -318,7 +392,15 @@ extern "C" int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, con
     else {
         const size_t smem = ((size_t)k * k * Cin + 8 * 64) * sizeof(float);
         EVFLY_REQUIRE(smem <= 48 * 1024, "patch_embed_ln_bf16: patch of %d values does not fit shared memory", k * k * Cin);
-        EVFLY_REQUIRE(total < (1ll << 31), "patch_embed_ln_bf16: too many tokens");
+        EVFLY_REQUIRE(total < (1ll << 28), "patch_embed_ln_bf16: too many tokens");
+        if (total <= 64 && k * k * Cin >= 512 && k * k * Cin <= 4096) {
+            // a handful of tokens with a long reduction: 8-CTA cluster per token (split K, DSMEM reduction)
+            k_patch_embed_ln_cluster<<<(unsigned)total * 8, 256, 0, (cudaStream_t)stream>>>(
+                reinterpret_cast<const __nv_bfloat16*>(d_x), d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), H, W, Cin, Cout,
+                k, stride, pad, OH, OW, eps);
+            EVFLY_LAUNCHED();
+            return EVFLY_OK;
+        }
         k_patch_embed_ln_block<<<(unsigned)total, 256, smem, (cudaStream_t)stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(d_x), d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), H, W, Cin, Cout,
             k, stride, pad, OH, OW, eps);
@@ -343,7 +425,7 @@ extern "C" int evfly_attention_small_bf16(const void* d_q, const void* d_kv, voi
                   "attention_small_bf16: bad argument (head dim <= 32, n_kv <= 8)");
     if (B == 0) return EVFLY_OK;
     const long long total = B * N * heads;
-    k_attention_small_bf16<<<(unsigned)ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
+    k_attention_small_bf16<<<(unsigned)ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(d_q), reinterpret_cast<const __nv_bfloat16*>(d_kv), reinterpret_cast<__nv_bfloat16*>(d_out), B, N, C, heads, n_kv);
     EVFLY_LAUNCHED();
     return EVFLY_OK;

@@ -297,6 +297,12 @@ int evfly_form_input_f32(float* d_x, float* d_out, int64_t n, int64_t plane, int
 int evfly_lstm_seq_f32(const float* d_gx, const float* d_whh_t, const float* d_h0, const float* d_c0,
                        float* d_hs, float* d_hT, float* d_cT, int T, int H, int n_seq, void* stream);
 
+/* LSTM cell update for n rows (gate order i,f,g,o): gates [n,4H] = x W_ih^T + h W_hh^T + biases (two
+ * evfly_linear_smallm_f32 calls), c_in [n,H] or NULL (zeros) -> c_out, h_out (and h_out2 if not NULL).
+ * The short-sequence / batch-1 form of evfly_lstm_seq_f32: the gate GEMV spreads over many CTAs.   */
+int evfly_lstm_pointwise_f32(const float* d_gates, const float* d_c_in, float* d_c_out, float* d_h_out,
+                             float* d_h_out2, int n, int H, void* stream);
+
 /* ConvLSTM cell pointwise (convlstm.py:44-53), gate order i,f,o,g: gates [4*Ch, P],
  * c [Ch,P] updated in place, h_out [Ch,P]:  c = sig(f)*c + sig(i)*tanh(g);  h = sig(o)*tanh(c).  */
 int evfly_convlstm_pointwise_f32(const float* d_gates, float* d_c, float* d_h_out, int Ch, int P,
