@@ -51,7 +51,9 @@ struct TcCfg {
     static constexpr int A_BYTES = BM * KC * 2;
     static constexpr int B_BYTES = TN * KC * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (STAGE_BYTES * 6 <= 200 * 1024) ? 6 : (STAGE_BYTES * 4 <= 200 * 1024 ? 4 : 3);
+    // as many stages as fit ~192 KB (max 10): narrow tiles have small stages and a latency-bound K loop
+    static constexpr int STAGES_FIT = (192 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 10 ? 10 : (STAGES_FIT < 3 ? 3 : STAGES_FIT);
     static constexpr int NACC = (TN <= 64) ? 4 : 2;            // TMEM accumulator buffers
     static constexpr int BIAS_FLOATS = 2048;                   // bias of every GEMM column, staged once per CTA
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_FLOATS * 4;
