@@ -24,6 +24,11 @@
 
 namespace evfly {
 
+// sigmoid / tanh on the fast exponential (2 ulp __expf + approximate reciprocal): ~1e-6 absolute, far below the
+// bf16 rounding of h; libdevice tanhf costs ~10x more and made the fused ConvLSTM epilogue the bottleneck
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
 // ---------------------------------------------------------------------------------------
 struct TcArgs {
     const float* bias;     // fp32 [bias_len] or nullptr; indexed by (n % bias_mod)
@@ -35,6 +40,11 @@ struct TcArgs {
     float* out_f32;        // optional fp32 destination instead (same addressing)
     long long M_rows;      // rows of the source pitch grid
     long long a_row0;      // first row of this problem inside the tensor map_a describes (ConvLSTM scan)
+    // persistent scan: the kernel runs n_steps dependent problems; per step the A rows, res and lstm_h advance
+    // by these strides and all CTAs meet at a grid-wide barrier (sync_counter) between steps
+    int n_steps;
+    long long a_row_step, res_step, lstm_h_step;
+    unsigned int* sync_counter;
     int Cin, n_rows;       // K per tap; GEMM N (rows of the weight matrix)
     int taps, w_pitch;     // 1 or 9; pixels per grid row (the kh shift)
     int relu;
@@ -63,7 +73,7 @@ struct TcCfg {
 };
 
 template <int TN, int KC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs p) {
     using Cfg = TcCfg<TN, KC>;
     extern __shared__ uint8_t smem_raw[];
@@ -113,21 +123,34 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ================= TMA producer =================
         int stage = 0;
         uint32_t phase = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const long long mt = tile / n_tiles;
-            const int nt = (int)(tile - mt * n_tiles);
-            const long long m0 = mt * Cfg::BM;
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
-                const int kh = tap / 3, kw = tap - kh * 3;  // taps == 1 -> 0,0
-                const long long row = p.a_row0 + m0 + (long long)kh * p.w_pitch + kw;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                uint8_t* sb = sa + Cfg::A_BYTES;
-                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                tma_load_2d(sa, &map_a, &full_bar[stage], kc * KC, (int)row);
-                tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * KC, nt * TN);
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        for (int step = 0; step < p.n_steps; ++step) {
+            if (step > 0) {
+                // grid barrier: every CTA's epilogue has published h_{step-1} (generic-proxy stores + __threadfence +
+                // atomic); acquire it, then order the async-proxy TMA reads after the acquire
+                const unsigned target = (unsigned)step * gridDim.x;
+                unsigned seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_counter) : "memory");
+                } while (seen < target);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            const long long row_base = p.a_row0 + (long long)step * p.a_row_step;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const long long mt = tile / n_tiles;
+                const int nt = (int)(tile - mt * n_tiles);
+                const long long m0 = mt * Cfg::BM;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+                    const int kh = tap / 3, kw = tap - kh * 3;  // taps == 1 -> 0,0
+                    const long long row = row_base + m0 + (long long)kh * p.w_pitch + kw;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &map_a, &full_bar[stage], kc * KC, (int)row);
+                    tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * KC, nt * TN);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -137,6 +160,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        for (int step = 0; step < p.n_steps; ++step)
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
             tc_fence_after();
@@ -160,10 +184,20 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
-        const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        // two groups of 4 warps (4-7, 8-11) alternate over this CTA's tiles: one warp per SM sub-partition is
+        // latency-bound on the epilogue of small-K problems (ViT Linear layers, ConvLSTM steps)
+        const int ew = (warp - 4) & 3;  // TMEM lanes [32*ew, 32*ew+32): a warp may only touch the lanes of warp % 4
+        const int grp = (warp - 4) >> 2;
+        const long long n_local = total_tiles > (long long)blockIdx.x ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        for (int step = 0; step < p.n_steps; ++step) {
+        const float* res_step = p.res ? p.res + (long long)step * p.res_step : nullptr;
+        __nv_bfloat16* lstm_h_step = p.lstm_h ? p.lstm_h + (long long)step * p.lstm_h_step : nullptr;
+        for (long long j = 0; j < n_local; ++j) {
+            const long long it = (long long)step * n_local + j;      // the MMA issuer's running tile counter
+            if ((int)(it & 1) != grp) continue;
+            const long long tile = blockIdx.x + j * gridDim.x;
+            const int acc = (int)(it % Cfg::NACC);
+            const uint32_t acc_phase = (uint32_t)((it / Cfg::NACC) & 1);
             const long long mt = tile / n_tiles;
             const int nt = (int)(tile - mt * n_tiles);
             const long long m = mt * Cfg::BM + ew * 32 + lane;
@@ -200,8 +234,8 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const float* sb = s_bias + n_first;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
-                    if (p.res) {
-                        const float* rp = p.res + m * (long long)p.n_rows + n_first;
+                    if (res_step) {
+                        const float* rp = res_step + m * (long long)p.n_rows + n_first;
                         if (n_first + 32 <= p.n_rows && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
@@ -247,10 +281,9 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         float cn[8], hn[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const float ig = 1.f / (1.f + __expf(-v[4 * q])), fg = 1.f / (1.f + __expf(-v[4 * q + 1]));
-                            const float og = 1.f / (1.f + __expf(-v[4 * q + 2]));
-                            cn[q] = fg * cin[q] + ig * tanhf(v[4 * q + 3]);
-                            hn[q] = og * tanhf(cn[q]);
+                            const float ig = fast_sigmoid(v[4 * q]), fg = fast_sigmoid(v[4 * q + 1]), og = fast_sigmoid(v[4 * q + 2]);
+                            cn[q] = fg * cin[q] + ig * fast_tanh(v[4 * q + 3]);
+                            hn[q] = og * fast_tanh(cn[q]);
                         }
                         *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                         *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
@@ -259,7 +292,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         __nv_bfloat162 t2 = __floats2bfloat162_rn(hn[4], hn[5]), t3 = __floats2bfloat162_rn(hn[6], hn[7]);
                         pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
                         pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                        *reinterpret_cast<uint4*>(p.lstm_h + m * (long long)Ch + ch0l) = pk;
+                        *reinterpret_cast<uint4*>(lstm_h_step + m * (long long)Ch + ch0l) = pk;
                     } else
                     if (p.out_f32) {
                         float* o = p.out_f32 + dst_pix * p.out_ld + p.out_c0 + ch0;
@@ -295,7 +328,16 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+        }
+        if (p.n_steps > 1) {
+            // publish this CTA's share of h_step: stores -> gpu-scope fence -> (all 8 epilogue warps) -> one atomic
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 128) {
+                __threadfence();   // cumulative: orders the other epilogue threads' (fenced, barrier-ordered) stores too
+                atomicAdd(p.sync_counter, 1u);
+            }
+        }
         }
     }
     tc_fence_before();
@@ -353,7 +395,7 @@ static int launch_tc_maps(const CUtensorMap& map_a, const CUtensorMap& map_b, co
     }
     const long long tiles = ceil_div(p.M_rows, Cfg::BM) * ceil_div(p.n_rows, TN);
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    k_tc_conv_bf16<TN, KC><<<grid, 256, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
+    k_tc_conv_bf16<TN, KC><<<grid, 384, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }
@@ -396,6 +438,9 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     p.out_f32 = a.out_f32;
     p.M_rows = a.M_rows;
     p.a_row0 = 0;
+    p.n_steps = 1;
+    p.a_row_step = p.res_step = p.lstm_h_step = 0;
+    p.sync_counter = nullptr;
     p.Cin = a.Cin;
     p.n_rows = a.n_rows;
     p.taps = a.taps;
@@ -436,15 +481,18 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
 // step kernels (h-gates GEMM + x-gates + cell update, see lstm_c above) are enqueued back to back from C++.
 // d_h_all bf16 [(T+1)*P, Ch]: block 0 holds h_0 on entry, block t+1 receives h_t.
 extern "C" int evfly_convlstm_scan_bf16(void* d_h_all, const void* d_wh, const float* d_gx, float* d_c, int T, int64_t P, int Ch,
-                                        void* stream) {
+                                        void* d_sync, void* stream) {
     EVFLY_REQUIRE(d_h_all && d_wh && d_gx && d_c && T >= 0 && P > 0 && Ch > 0 && Ch % 64 == 0 && 4 * Ch <= 2048, "convlstm_scan_bf16: bad argument (Ch %% 64 == 0, 4*Ch <= 2048)");
     if (T == 0) return EVFLY_OK;
-    constexpr int TN = 32, KC = 64;
-    using Cfg = TcCfg<TN, KC>;
+    constexpr int KC = 64;
+    // N tile as in evfly_tc_conv_bf16: the widest that still gives >= 148 tiles per step
+    const long long m_tiles = ceil_div(P, 128);
+    int tn = 256;
+    while (tn > 32 && m_tiles * ceil_div(4 * Ch, tn) < kNumSMs) tn >>= 1;
     CUtensorMap map_a, map_b;
-    int rc = make_map_2d(&map_a, d_h_all, (uint64_t)(T + 1) * P, (uint64_t)Ch, (uint64_t)Ch, Cfg::BM, KC);
+    int rc = make_map_2d(&map_a, d_h_all, (uint64_t)(T + 1) * P, (uint64_t)Ch, (uint64_t)Ch, 128, KC);
     if (rc) return rc;
-    rc = make_map_2d(&map_b, d_wh, (uint64_t)4 * Ch, (uint64_t)Ch, (uint64_t)Ch, TN, KC);
+    rc = make_map_2d(&map_b, d_wh, (uint64_t)4 * Ch, (uint64_t)Ch, (uint64_t)Ch, (uint32_t)tn, KC);
     if (rc) return rc;
     TcArgs p;
     memset(&p, 0, sizeof(p));
@@ -456,11 +504,33 @@ extern "C" int evfly_convlstm_scan_bf16(void* d_h_all, const void* d_wh, const f
     p.out_ld = 4 * Ch;
     p.lstm_c = d_c;
     __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(d_h_all);
+    cudaStream_t st = (cudaStream_t)stream;
+    p.n_steps = 1;
+    if (d_sync) {
+        // persistent: ONE launch walks all T steps; CTAs meet at a grid-wide barrier between steps. The grid is
+        // at most 148 CTAs of 1 CTA/SM, so all of them are co-resident and the spin-wait cannot deadlock.
+        EVFLY_CUDA(cudaMemsetAsync(d_sync, 0, 8, st));
+        p.n_steps = T;
+        p.a_row0 = 0;
+        p.a_row_step = P;
+        p.res = d_gx;
+        p.res_step = (long long)P * 4 * Ch;
+        p.lstm_h = h + (long long)P * Ch;
+        p.lstm_h_step = (long long)P * Ch;
+        p.sync_counter = reinterpret_cast<unsigned int*>(d_sync);
+        return tn == 32 ? launch_tc_maps<32, KC>(map_a, map_b, p, st)
+             : tn == 64 ? launch_tc_maps<64, KC>(map_a, map_b, p, st)
+             : tn == 128 ? launch_tc_maps<128, KC>(map_a, map_b, p, st)
+                         : launch_tc_maps<256, KC>(map_a, map_b, p, st);
+    }
     for (int t = 0; t < T; ++t) {
         p.a_row0 = (long long)t * P;
         p.res = d_gx + (long long)t * P * 4 * Ch;
         p.lstm_h = h + (long long)(t + 1) * P * Ch;
-        rc = launch_tc_maps<TN, KC>(map_a, map_b, p, (cudaStream_t)stream);
+        rc = tn == 32 ? launch_tc_maps<32, KC>(map_a, map_b, p, st)
+           : tn == 64 ? launch_tc_maps<64, KC>(map_a, map_b, p, st)
+           : tn == 128 ? launch_tc_maps<128, KC>(map_a, map_b, p, st)
+                       : launch_tc_maps<256, KC>(map_a, map_b, p, st);
         if (rc) return rc;
     }
     return EVFLY_OK;

@@ -15,6 +15,7 @@ from . import _lib
 
 BF16 = torch.bfloat16
 USE_HALO = True     # small-channel 3x3 convs through the halo-reuse kernel
+PERSISTENT_SCAN = True   # ConvLSTM recurrence as one persistent launch with a grid barrier per step
 
 
 @dataclass
@@ -129,7 +130,8 @@ def convlstm_step(h_prev, wh_packed, gx_t, c_f32, h_out):
 
 def convlstm_scan(h_all, wh_packed, gx, c_f32, T, P, Ch):
     """h_all bf16 [(T+1), P, Ch] (block 0 = h_0), gx fp32 [T*P, 4Ch], c fp32 [P,Ch]: the whole recurrence in one call."""
-    _call_scan(h_all.data_ptr(), wh_packed.data_ptr(), _lib.ptr(gx), _lib.ptr(c_f32), T, P, Ch)
+    sync = torch.empty((1,), dtype=torch.int64, device=c_f32.device) if PERSISTENT_SCAN else None
+    _call_scan(h_all.data_ptr(), wh_packed.data_ptr(), _lib.ptr(gx), _lib.ptr(c_f32), T, P, Ch, _lib.ptr(sync))
 
 
 def conv_transpose2x2(g: Grid, w_packed, bias, out_data: torch.Tensor, out_c0: int):

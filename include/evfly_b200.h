@@ -357,9 +357,11 @@ int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream);
 /* ConvLSTM (1x1 kernel, no bias) recurrence over T steps in one call (convlstm.py:136-176 loops in Python):
  * d_h_all bf16 [(T+1)*P, Ch] holds h_0 in block 0 and receives h_t in block t+1; d_gx fp32 [T*P, 4*Ch] are the
  * x-gate pre-activations, d_wh bf16 [4*Ch, Ch] the h half of the gate conv, both with gate-interleaved
- * rows/columns n = 4*ch + gate (i,f,o,g); d_c fp32 [P, Ch] is updated in place. T fused step kernels.      */
+ * rows/columns n = 4*ch + gate (i,f,o,g); d_c fp32 [P, Ch] is updated in place.
+ * d_sync != NULL (8 bytes of device scratch): ONE persistent launch walks the T steps, the <= 148 co-resident
+ * CTAs meeting at a grid-wide barrier between steps; d_sync == NULL: T fused step kernels back to back.     */
 int evfly_convlstm_scan_bf16(void* d_h_all, const void* d_wh, const float* d_gx, float* d_c, int T, int64_t P,
-                             int Ch, void* stream);
+                             int Ch, void* d_sync, void* stream);
 
 /* First UNet layer (Cin = 1 or 2, so K = 9 or 18: CUDA cores): fp32 NCHW [N,Cin,H,W] -> 3x3 valid
  * conv + bias + ReLU -> bf16 NHWC [N,H,W,32] on the input's own grid (valid (H-2)x(W-2)).

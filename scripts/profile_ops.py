@@ -1,0 +1,40 @@
+"""Warm per-entry-point timing of one bench step (CUDA events around every C-ABI call, aggregated by name).
+Unlike an ncu launch list the caches are warm and the kernels overlap as in production; event overhead is
+a few microseconds per call. Usage: python scripts/profile_ops.py [trajectories|pipeline]"""
+import collections, json, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from evfly_b200 import _lib
+
+name = sys.argv[1] if len(sys.argv) > 1 else "trajectories"
+torch.cuda.set_device(0)
+wl = bench.WORKLOADS[name](0, torch.device("cuda", 0))
+for i in range(3):
+    wl.step(i)
+torch.cuda.synchronize()
+lib = _lib.load()
+records = collections.defaultdict(list)
+orig = {}
+for fn in _lib.SIGNATURES:
+    if fn in ("evfly_last_error", "evfly_abi_version", "evfly_launch_count") or fn.endswith("_bytes"):
+        continue
+    f = getattr(lib, fn)
+    orig[fn] = f
+    def make(fn, f):
+        def wrapped(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); rc = f(*a); e1.record()
+            records[fn].append((e0, e1))
+            return rc
+        return wrapped
+    setattr(lib, fn, make(fn, f))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(); wl.step(3); b.record()
+torch.cuda.synchronize()
+total = a.elapsed_time(b)
+rows = sorted(((sum(x.elapsed_time(y) for x, y in v), len(v), k) for k, v in records.items()), reverse=True)
+acc = sum(r[0] for r in rows)
+print(json.dumps({"workload": name, "step_ms_instrumented": total, "sum_of_calls_ms": acc}))
+for ms, n, k in rows[:24]:
+    print(f"{ms:8.3f} ms {n:5d} calls {100 * ms / total:5.1f}%  {k}")

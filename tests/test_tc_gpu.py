@@ -223,3 +223,31 @@ def test_halo_conv_equals_reference_and_streaming_kernel(cuda_lib, N, H, W, vh, 
     finally:
         tc.USE_HALO = True
     assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()      # same math, different accumulation order
+
+
+@pytest.mark.parametrize("T,P,Ch", [(12, 204, 512), (7, 816, 512), (3, 100, 64)])
+def test_persistent_convlstm_scan_equals_per_step_launches(cuda_lib, T, P, Ch):
+    wh = tc.pack_convlstm_gate_weight((rnd(4 * Ch, Ch, seed=1, scale=Ch ** -0.5)).cuda())
+    gx = rnd(T * P, 4 * Ch, seed=2).cuda()
+    h0 = (rnd(P, Ch, seed=3) * 0.3).to(BF).cuda()
+    outs = []
+    for persistent in (True, False):
+        tc.PERSISTENT_SCAN = persistent
+        try:
+            h_all = torch.empty((T + 1, P, Ch), dtype=BF, device="cuda")
+            h_all[0].copy_(h0)
+            c = torch.zeros((P, Ch), device="cuda")
+            tc.convlstm_scan(h_all, wh, gx, c, T, P, Ch)
+            torch.cuda.synchronize()
+            outs.append((h_all.clone(), c.clone()))
+        finally:
+            tc.PERSISTENT_SCAN = True
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])     # same arithmetic, bit-identical
+    # and both follow the recurrence (fp64 reference on the bf16-rounded operands)
+    w = wh.float().cpu().double()
+    h, cc = h0.float().cpu().double(), torch.zeros(P, Ch, dtype=torch.float64)
+    for t in range(T):
+        g = (h @ w.t() + gx[t * P:(t + 1) * P].cpu().double()).view(P, Ch, 4)
+        cc = torch.sigmoid(g[..., 1]) * cc + torch.sigmoid(g[..., 0]) * torch.tanh(g[..., 3])
+        h = (torch.sigmoid(g[..., 2]) * torch.tanh(cc)).to(BF).double()
+    check_bf16(outs[0][0][T], h, "scan h_T")
