@@ -34,6 +34,8 @@ SIGNATURES = {
     "evfly_pack_events_f64": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _f64, _f64, _i64, _vp, _vp, _vp, _vp]),
     "evfly_pack_events_soa": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "evfly_accumulate_counts": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "evfly_accumulate_counts_binned_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "evfly_accumulate_counts_binned": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "evfly_counts_to_frame_f64": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _vp]),
     "evfly_counts_to_u8": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "evfly_u8_saturate_replay": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),

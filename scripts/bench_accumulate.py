@@ -47,7 +47,11 @@ def main():
 
         def counts_only(i):
             counts.zero_()
-            L1.accumulate_counts(recs[i & 1], H, W, out=counts)
+            L1.accumulate_counts(recs[i & 1], H, W, out=counts, algo="red")
+
+        def counts_binned(i):
+            counts.zero_()
+            L1.accumulate_counts(recs[i & 1], H, W, out=counts, algo="binned")
 
         def direct(i):
             counts.zero_(); voxel.zero_()
@@ -60,6 +64,7 @@ def main():
             L1.voxelize_window(recs[i & 1], H, W, B, 0, 33_333_333, counts=None, voxel=voxel, ws=ws, algo=1, want_counts=False)
 
         for name, fn, bytes_ in (("counts_only", counts_only, 16 * n + 2 * H * W * 4),
+                                 ("counts_binned", counts_binned, 16 * n + 2 * H * W * 4),
                                  ("voxel_direct", direct, 16 * n + 7 * H * W * 4),
                                  ("voxel_staged", staged, 16 * n + 7 * H * W * 4),
                                  ("voxel_staged_noCounts", staged_voxel_only, 16 * n + 5 * H * W * 4)):
