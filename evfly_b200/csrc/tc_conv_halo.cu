@@ -34,10 +34,11 @@ struct HaloCfg {
     static constexpr int HALO_BYTES = ((HALO_ROWS * ROW_B + 1023) / 1024) * 1024;
     static constexpr int W_TAP_BYTES = COUT * ROW_B;
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = (COUT > 64) ? 3 : 4;          // 64->128: 144 KB of resident weights leave room for 3 halos
     static constexpr int NACC = 4;
-    static constexpr int TMEM_COLS = (NACC * COUT <= 128) ? 128 : 256;
-    static constexpr int SMEM_BYTES = W_BYTES + STAGES * HALO_BYTES + 1024 + 512;
+    static constexpr int TMEM_COLS = (NACC * COUT <= 128) ? 128 : (NACC * COUT <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = W_BYTES + STAGES * HALO_BYTES + 1024 + 1024;
+    static_assert(SMEM_BYTES <= 227 * 1024, "halo conv: weights + halo stages exceed shared memory");
     static constexpr uint32_t LAYOUT = (CIN == 64) ? kLayoutSw128 : kLayoutSw64;
     static constexpr uint32_t SBO_A = 10 * ROW_B;               // next 8-pixel group = next output row = 10 halo rows
     static constexpr uint32_t SBO_B = 8 * ROW_B;
@@ -145,9 +146,12 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int grp = (warp - 4) >> 2;
         const int row = ew * 32 + lane;          // tile pixel: r = row / 8, c = row % 8
         const int r = row >> 3, c = row & 7;
-        float breg[COUT];                        // bias in registers (same for every tile)
+        constexpr bool kBiasRegs = COUT <= 64;   // bias in registers (same for every tile); from shared memory for wide outputs
+        float breg[kBiasRegs ? COUT : 1];
+        if constexpr (kBiasRegs) {
 #pragma unroll
-        for (int j = 0; j < COUT; ++j) breg[j] = s_bias[j];
+            for (int j = 0; j < COUT; ++j) breg[j] = s_bias[j];
+        }
         int it = grp;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
             const int acc = it & (Cfg::NACC - 1);
@@ -171,7 +175,7 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float x = __uint_as_float(v[q * 8 + e]) + breg[c0 + q * 8 + e];
+                            const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
                             f[e] = p.relu ? fmaxf(x, 0.f) : x;
                         }
                         uint4 pk;
@@ -261,7 +265,8 @@ using namespace evfly;
 extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int Hp, int Wp,
                                           int vh, int vw, int Cin, int Cout, int relu, void* stream) {
     EVFLY_REQUIRE(d_x && d_w && d_out && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
-    EVFLY_REQUIRE((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64), "tc_conv3x3_halo_bf16: Cin, Cout must be 32 or 64 (got %d, %d)", Cin, Cout);
+    EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128),
+                  "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64} or (64,128) (got %d, %d)", Cin, Cout);
     HaloArgs p;
     p.bias = d_bias;
     p.out = reinterpret_cast<__nv_bfloat16*>(d_out);
@@ -275,6 +280,7 @@ extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, cons
     p.relu = relu;
     EVFLY_REQUIRE((long long)p.tiles_x * p.tiles_y * N < (1ll << 31), "tc_conv3x3_halo_bf16: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 64 && Cout == 128) return launch_halo<64, 128>(d_x, d_w, p, st);
     if (Cin == 32 && Cout == 32) return launch_halo<32, 32>(d_x, d_w, p, st);
     if (Cin == 32 && Cout == 64) return launch_halo<32, 64>(d_x, d_w, p, st);
     if (Cin == 64 && Cout == 32) return launch_halo<64, 32>(d_x, d_w, p, st);

@@ -73,7 +73,7 @@ def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None) -> Grid
     Cout = w_packed.shape[0]
     if out is None:
         out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
-    if USE_HALO and g.C in (32, 64) and Cout in (32, 64):
+    if USE_HALO and ((g.C in (32, 64) and Cout in (32, 64)) or (g.C == 64 and Cout == 128)):
         # small-channel layers: halo reuse from shared memory, weights resident (tc_conv_halo.cu)
         _call_halo(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C, Cout, int(relu))
         return out

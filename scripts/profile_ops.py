@@ -15,6 +15,7 @@ for i in range(3):
 torch.cuda.synchronize()
 lib = _lib.load()
 records = collections.defaultdict(list)
+shapes = collections.defaultdict(list)
 orig = {}
 for fn in _lib.SIGNATURES:
     if fn in ("evfly_last_error", "evfly_abi_version", "evfly_launch_count") or fn.endswith("_bytes"):
@@ -26,6 +27,9 @@ for fn in _lib.SIGNATURES:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); rc = f(*a); e1.record()
             records[fn].append((e0, e1))
+            if fn == "evfly_tc_conv_bf16":       # per-shape breakdown of the GEMM family
+                st = a[0]._obj if hasattr(a[0], "_obj") else a[0].contents
+                shapes[(st.M_rows, st.Cin, st.n_rows, st.taps, st.convt, st.Hp, st.Wp)].append((e0, e1))
             return rc
         return wrapped
     setattr(lib, fn, make(fn, f))
@@ -38,3 +42,10 @@ acc = sum(r[0] for r in rows)
 print(json.dumps({"workload": name, "step_ms_instrumented": total, "sum_of_calls_ms": acc}))
 for ms, n, k in rows[:24]:
     print(f"{ms:8.3f} ms {n:5d} calls {100 * ms / total:5.1f}%  {k}")
+
+print("evfly_tc_conv_bf16 by shape (M_rows, Cin, Cout_rows, taps, convt, Hp, Wp):")
+for k, v in sorted(shapes.items(), key=lambda kv: -sum(x.elapsed_time(y) for x, y in kv[1])):
+    ms = sum(x.elapsed_time(y) for x, y in v)
+    M, Cin, n_rows, taps = k[0], k[1], k[2], k[3]
+    tf = 2.0 * M * Cin * taps * n_rows * len(v) / ms / 1e9
+    print(f"{ms:8.3f} ms {len(v):3d} calls {tf:7.1f} TFLOP/s  {k}")

@@ -206,7 +206,8 @@ def test_shifted_descriptor_probe(cuda_lib):
 
 
 @pytest.mark.parametrize("N,H,W,vh,vw,Cin,Cout", [(2, 20, 24, 20, 24, 32, 32), (1, 37, 29, 35, 27, 64, 64), (3, 19, 11, 19, 11, 32, 64),
-                                                  (1, 72, 152, 72, 152, 64, 32), (2, 18, 10, 18, 10, 32, 32), (1, 5, 5, 3, 3, 64, 64)])
+                                                  (1, 72, 152, 72, 152, 64, 32), (2, 18, 10, 18, 10, 32, 32), (1, 5, 5, 3, 3, 64, 64),
+                                                  (2, 41, 53, 40, 50, 64, 128), (1, 126, 170, 126, 169, 64, 128)])
 def test_halo_conv_equals_reference_and_streaming_kernel(cuda_lib, N, H, W, vh, vw, Cin, Cout):
     x = bf(rnd(N, Cin, vh, vw, seed=1))
     w = bf(rnd(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5))
