@@ -22,6 +22,8 @@ namespace evfly {
 struct HaloArgs {
     const float* bias;
     __nv_bfloat16* out;   // [N, Hp, Wp, COUT], same pitch as the input
+    __nv_bfloat16* pool_out;   // optional fused MaxPool2d(2): [N, Hp2, Wp2, COUT], valid (out_vh/2) x (out_vw/2)
+    int Hp2, Wp2;
     int N, Hp, Wp, out_vh, out_vw;
     int tiles_x, tiles_y;
     int relu;
@@ -43,6 +45,15 @@ struct HaloCfg {
     static constexpr uint32_t SBO_A = 10 * ROW_B;               // next 8-pixel group = next output row = 10 halo rows
     static constexpr uint32_t SBO_B = 8 * ROW_B;
 };
+
+__device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    return pk;
+}
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -162,6 +173,11 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const int oh = ty * 16 + r, ow = tx * 8 + c;
             const bool ok = oh < p.out_vh && ow < p.out_vw;
             __nv_bfloat16* o = p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT;
+            // fused 2x2 max-pool: the partners of pixel (r, c) are lanes ^1 (column) and ^8 (row) of the same warp;
+            // the lane with even r and even c writes. max commutes with the (monotonic) bf16 rounding, so the
+            // result is bit-identical to pooling the stored tensor.
+            const bool pool_lane = p.pool_out != nullptr && ((lane & 9) == 0) && oh + 1 < p.out_vh && ow + 1 < p.out_vw;
+            __nv_bfloat16* po = p.pool_out ? p.pool_out + (((long long)n * p.Hp2 + (oh >> 1)) * p.Wp2 + (ow >> 1)) * COUT : nullptr;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
 #pragma unroll
@@ -169,21 +185,22 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * COUT + c0), v);
                 tmem_ld_wait();
-                if (ok) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float f[8];
+                for (int q = 0; q < 4; ++q) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
+                        f[e] = p.relu ? fmaxf(x, 0.f) : x;
+                    }
+                    if (ok) reinterpret_cast<uint4*>(o + c0)[q] = pack8_bf16(f);
+                    if (p.pool_out) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
-                            f[e] = p.relu ? fmaxf(x, 0.f) : x;
+                            f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
+                            f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 8));
                         }
-                        uint4 pk;
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-                        __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                        reinterpret_cast<uint4*>(o + c0)[q] = pk;
+                        if (pool_lane) reinterpret_cast<uint4*>(po + c0)[q] = pack8_bf16(f);
                     }
                 }
             }
@@ -262,8 +279,8 @@ static int launch_halo(const void* x, const void* w, const HaloArgs& p, cudaStre
 
 using namespace evfly;
 
-extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int Hp, int Wp,
-                                          int vh, int vw, int Cin, int Cout, int relu, void* stream) {
+static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp, int Wp,
+                     int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream) {
     EVFLY_REQUIRE(d_x && d_w && d_out && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
     EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128),
                   "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64} or (64,128) (got %d, %d)", Cin, Cout);
@@ -278,6 +295,10 @@ extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, cons
     p.tiles_x = (p.out_vw + 7) / 8;
     p.tiles_y = (p.out_vh + 15) / 16;
     p.relu = relu;
+    p.pool_out = reinterpret_cast<__nv_bfloat16*>(d_pool);
+    p.Hp2 = Hp2;
+    p.Wp2 = Wp2;
+    EVFLY_REQUIRE(!d_pool || (Hp2 >= (vh - 2) / 2 && Wp2 >= (vw - 2) / 2), "tc_conv3x3_halo_pool_bf16: pooled grid smaller than (vh-2)/2 x (vw-2)/2");
     EVFLY_REQUIRE((long long)p.tiles_x * p.tiles_y * N < (1ll << 31), "tc_conv3x3_halo_bf16: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 64 && Cout == 128) return launch_halo<64, 128>(d_x, d_w, p, st);
@@ -285,4 +306,15 @@ extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, cons
     if (Cin == 32 && Cout == 64) return launch_halo<32, 64>(d_x, d_w, p, st);
     if (Cin == 64 && Cout == 32) return launch_halo<64, 32>(d_x, d_w, p, st);
     return launch_halo<64, 64>(d_x, d_w, p, st);
+}
+
+extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int Hp, int Wp,
+                                          int vh, int vw, int Cin, int Cout, int relu, void* stream) {
+    return halo_conv(d_x, d_w, d_bias, d_out, nullptr, N, Hp, Wp, vh, vw, Cin, Cout, relu, 0, 0, stream);
+}
+
+extern "C" int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp,
+                                               int Wp, int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream) {
+    EVFLY_REQUIRE(d_pool, "tc_conv3x3_halo_pool_bf16: null pool output");
+    return halo_conv(d_x, d_w, d_bias, d_out, d_pool, N, Hp, Wp, vh, vw, Cin, Cout, relu, Hp2, Wp2, stream);
 }

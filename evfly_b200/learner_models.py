@@ -363,11 +363,12 @@ class OrigUNet(PackedModule):
         N, dev = im.shape[0], im.device
         b = lambda name: getattr(self, "unet_" + name).bias
         cv = lambda g, name: tc.conv3x3(g, W[name], b(name), relu=True)
-        y_e1 = cv(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12")
-        y_e2 = cv(cv(tc.maxpool2x2(y_e1), "e21"), "e22")
-        y_e3 = cv(cv(tc.maxpool2x2(y_e2), "e31"), "e32")
-        y_e4 = cv(cv(tc.maxpool2x2(y_e3), "e41"), "e42")
-        y_e5 = cv(cv(tc.maxpool2x2(y_e4), "e51"), "e52")
+        cvp = lambda g, name: tc.conv3x3_pool(g, W[name], b(name), relu=True)     # conv + MaxPool2d(2), fused where it can be
+        y_e1, p1 = cvp(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12")
+        y_e2, p2 = cvp(cv(p1, "e21"), "e22")
+        y_e3, p3 = cvp(cv(p2, "e31"), "e32")
+        y_e4, p4 = cvp(cv(p3, "e41"), "e42")
+        y_e5 = cv(cv(p4, "e51"), "e52")
 
         h_unet = None
         if self.num_recurrent[0] > 0:

@@ -14,7 +14,8 @@ import torch
 from . import _lib
 
 BF16 = torch.bfloat16
-USE_HALO = True     # small-channel 3x3 convs through the halo-reuse kernel
+USE_HALO = True      # small-channel 3x3 convs through the halo-reuse kernel
+FUSE_POOL = True     # MaxPool2d(2) in the epilogue of the halo-reuse kernel
 PERSISTENT_SCAN = True   # ConvLSTM recurrence as one persistent launch with a grid barrier per step
 
 
@@ -64,6 +65,29 @@ def _call_halo(*args):
     _lib.check(_lib.load().evfly_tc_conv3x3_halo_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_bf16")
 
 
+def _call_halo_pool(*args):
+    _lib.check(_lib.load().evfly_tc_conv3x3_halo_pool_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_pool_bf16")
+
+
+def _halo_ok(cin, cout):
+    return USE_HALO and ((cin in (32, 64) and cout in (32, 64)) or (cin == 64 and cout == 128))
+
+
+def conv3x3_pool(g: Grid, w_packed, bias, relu=True):
+    """conv3x3 followed by MaxPool2d(2): returns (conv output, pooled output). The pool is fused into the conv
+    epilogue on the halo path, a separate pass otherwise; the two are bit-identical."""
+    Cout = w_packed.shape[0]
+    if not (_halo_ok(g.C, Cout) and FUSE_POOL):
+        y = conv3x3(g, w_packed, bias, relu=relu)
+        return y, maxpool2x2(y)
+    out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
+    ph, pw = (g.vh - 2) // 2, (g.vw - 2) // 2
+    pooled = new_grid(g.N, ph, pw, Cout, ph, pw, g.data.device)
+    _call_halo_pool(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), pooled.data.data_ptr(), g.N, g.Hp, g.Wp,
+                    g.vh, g.vw, g.C, Cout, int(relu), pooled.Hp, pooled.Wp)
+    return out, pooled
+
+
 def _call(a: _lib.TcConvArgs):
     _lib.check(_lib.load().evfly_tc_conv_bf16(C.byref(a), _lib.stream_ptr()), "evfly_tc_conv_bf16")
 
@@ -73,7 +97,7 @@ def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None) -> Grid
     Cout = w_packed.shape[0]
     if out is None:
         out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
-    if USE_HALO and ((g.C in (32, 64) and Cout in (32, 64)) or (g.C == 64 and Cout == 128)):
+    if _halo_ok(g.C, Cout):
         # small-channel layers: halo reuse from shared memory, weights resident (tc_conv_halo.cu)
         _call_halo(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C, Cout, int(relu))
         return out

@@ -436,6 +436,13 @@ int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float
 int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N,
                                int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, void* stream);
 
+/* The same conv with nn.MaxPool2d(2) (learner_models.py OrigUNet pool1..pool4) fused into the epilogue: besides
+ * d_out it writes d_pool bf16 [N,Hp2,Wp2,Cout], valid ((vh-2)/2) x ((vw-2)/2), bit-identical to
+ * evfly_maxpool2x2_nhwc_bf16 applied to d_out (saves re-reading the full-resolution activation).       */
+int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool,
+                                    int N, int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2,
+                                    void* stream);
+
 /* Hardware probe (diagnostic): D = x[shift : shift+128] @ w^T computed by tcgen05.mma from ONE TMA-loaded
  * [136, KC] tile whose descriptor starts `shift` rows into the swizzle atom (base-offset field set when
  * use_base_offset). x bf16 [136,KC], w bf16 [32,KC], out fp32 [128,32]. KC in {32 (64B swizzle), 64 (128B)}. */

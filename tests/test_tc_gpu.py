@@ -226,6 +226,25 @@ def test_halo_conv_equals_reference_and_streaming_kernel(cuda_lib, N, H, W, vh, 
     assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()      # same math, different accumulation order
 
 
+@pytest.mark.parametrize("N,vh,vw,Cin,Cout", [(2, 20, 24, 32, 32), (1, 37, 29, 64, 64), (3, 19, 13, 32, 64), (1, 71, 150, 64, 128), (1, 4, 4, 32, 32)])
+def test_halo_conv_fused_maxpool_is_bit_identical_to_separate_pool(cuda_lib, N, vh, vw, Cin, Cout):
+    """learner_models.py OrigUNet: pool(relu(conv(x))). The fused epilogue pools fp32 values before rounding to bf16;
+    rounding is monotonic, so the result must equal the stand-alone pool of the stored bf16 tensor bit for bit."""
+    x = bf(rnd(N, Cin, vh, vw, seed=4))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=5, scale=(9 * Cin) ** -0.5))
+    b = rnd(Cout, seed=6)
+    g = tc.nchw_to_grid(x.cuda(), vh, vw)
+    wp = tc.pack_conv3x3_weight(w.cuda())
+    y, pooled = tc.conv3x3_pool(g, wp, b.cuda(), relu=True)
+    assert (pooled.vh, pooled.vw) == ((vh - 2) // 2, (vw - 2) // 2)
+    y2 = tc.conv3x3(g, wp, b.cuda(), relu=True)
+    assert torch.equal(tc.grid_to_nchw(y.data, vh - 2, vw - 2), tc.grid_to_nchw(y2.data, vh - 2, vw - 2))
+    want = tc.maxpool2x2(y2)
+    assert torch.equal(tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw), tc.grid_to_nchw(want.data, want.vh, want.vw))
+    ref = F.max_pool2d(F.relu(F.conv2d(x.double(), w.double(), b.double())), 2)
+    check_bf16(tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw), ref, "fused pool")
+
+
 @pytest.mark.parametrize("T,P,Ch", [(12, 204, 512), (7, 816, 512), (3, 100, 64)])
 def test_persistent_convlstm_scan_equals_per_step_launches(cuda_lib, T, P, Ch):
     wh = tc.pack_convlstm_gate_weight((rnd(4 * Ch, Ch, seed=1, scale=Ch ** -0.5)).cuda())
