@@ -92,6 +92,7 @@ SIGNATURES.update({
     "evfly_tc_conv_bf16": (_i32, [C.POINTER(TcConvArgs), _vp]),
     "evfly_convlstm_scan_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "evfly_stem_conv3x3_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_stem_conv3x3_fma_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "evfly_maxpool2x2_nhwc_bf16": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_resize_bilinear_nhwc_bf16": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i32, _vp]),
     "evfly_crop_nhwc_bf16": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i32, _vp]),

@@ -191,9 +191,9 @@ k_nhwc_to_nchw_f32(const void* __restrict__ x, int src_is_f32, float* __restrict
 using namespace evfly;
 static inline int g_ew(long long n) { return stream_grid(n, 256 * 2, 16); }
 
-extern "C" int evfly_stem_conv3x3_bf16(const float* d_x, const float* d_w, const float* d_bias, void* d_out, int N, int Cin,
+extern "C" int evfly_stem_conv3x3_fma_bf16(const float* d_x, const float* d_w, const float* d_bias, void* d_out, int N, int Cin,
                                        int H, int W, void* stream) {
-    EVFLY_REQUIRE(d_x && d_w && d_bias && d_out && N >= 0 && (Cin == 1 || Cin == 2) && H >= 3 && W >= 3, "stem_conv3x3_bf16: bad argument (Cin must be 1 or 2)");
+    EVFLY_REQUIRE(d_x && d_w && d_bias && d_out && N >= 0 && (Cin == 1 || Cin == 2) && H >= 3 && W >= 3, "stem_conv3x3_fma_bf16: bad argument (Cin must be 1 or 2)");
     if (N == 0) return EVFLY_OK;
     k_stem_conv3x3<<<stream_grid((long long)N * H * W, 256, 16), 256, 0, (cudaStream_t)stream>>>(d_x, d_w, d_bias, reinterpret_cast<uint4*>(d_out), N, Cin, H, W);
     EVFLY_LAUNCHED();

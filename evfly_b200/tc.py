@@ -171,11 +171,14 @@ def conv_transpose2x2(g: Grid, w_packed, bias, out_data: torch.Tensor, out_c0: i
     _call(a)
 
 
-def stem_conv3x3(x_nchw_f32, w, bias) -> Grid:
+def stem_conv3x3(x_nchw_f32, w, bias, fma=False) -> Grid:
+    """UNet stem on the tensor cores (image and weights rounded to bf16); fma=True: fp32 CUDA-core version."""
     N, Cin, H, W = x_nchw_f32.shape
     out = new_grid(N, H, W, 32, H - 2, W - 2, x_nchw_f32.device)
-    _lib.check(_lib.load().evfly_stem_conv3x3_bf16(_lib.ptr(x_nchw_f32), _lib.ptr(w), _lib.ptr(bias), out.data.data_ptr(),
-                                                    N, Cin, H, W, _lib.stream_ptr()), "evfly_stem_conv3x3_bf16")
+    lib = _lib.load()
+    fn = lib.evfly_stem_conv3x3_fma_bf16 if fma else lib.evfly_stem_conv3x3_bf16
+    _lib.check(fn(_lib.ptr(x_nchw_f32), _lib.ptr(w), _lib.ptr(bias), out.data.data_ptr(), N, Cin, H, W, _lib.stream_ptr()),
+               "evfly_stem_conv3x3_bf16")
     return out
 
 

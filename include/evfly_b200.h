@@ -372,11 +372,18 @@ int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream);
 int evfly_convlstm_scan_bf16(void* d_h_all, const void* d_wh, const float* d_gx, float* d_c, int T, int64_t P,
                              int Ch, void* d_sync, void* stream);
 
-/* First UNet layer (Cin = 1 or 2, so K = 9 or 18: CUDA cores): fp32 NCHW [N,Cin,H,W] -> 3x3 valid
+/* First UNet layer (learner_models.py OrigUNet unet_e11, Cin = 1 or 2): fp32 NCHW [N,Cin,H,W] -> 3x3 valid
  * conv + bias + ReLU -> bf16 NHWC [N,H,W,32] on the input's own grid (valid (H-2)x(W-2)).
- * w fp32 [32,Cin,3,3] (PyTorch layout), bias fp32 [32].                                       */
+ * w fp32 [32,Cin,3,3] (PyTorch layout), bias fp32 [32]. Runs on tcgen05: every thread builds the im2col row
+ * of its pixel (K = 9*Cin zero-padded to 32, bf16) in swizzled shared memory, two MMAs per 128-pixel tile
+ * (evfly_b200/csrc/tc_stem.cu); bias is added in fp32.                                                     */
 int evfly_stem_conv3x3_bf16(const float* d_x, const float* d_w, const float* d_bias, void* d_out,
                             int N, int Cin, int H, int W, void* stream);
+
+/* The same layer on CUDA cores with fp32 inputs and weights (FMA-bound; kept as the cross-check of the tensor-core
+ * stem and for inputs whose bf16 rounding matters).                                                       */
+int evfly_stem_conv3x3_fma_bf16(const float* d_x, const float* d_w, const float* d_bias, void* d_out,
+                                int N, int Cin, int H, int W, void* stream);
 
 /* 2x2 stride-2 max-pool of the valid region of a bf16 NHWC pitch grid [N,Hp,Wp,C] (valid vh x vw)
  * into a compact grid [N, vh/2, vw/2, C]. C % 8 == 0.                                         */

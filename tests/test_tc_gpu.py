@@ -92,7 +92,12 @@ def test_nhwc_glue(cuda_lib):
     for cin in (1, 2):
         xs, ws, bs = rnd(2, cin, 30, 41, seed=2), rnd(32, cin, 3, 3, seed=3, scale=0.3), rnd(32, seed=4)
         out = tc.stem_conv3x3(xs.cuda(), ws.cuda(), bs.cuda())
-        check_bf16(tc.grid_to_nchw(out.data, 28, 39), F.relu(F.conv2d(xs, ws, bs)), "stem")
+        # the tensor-core stem rounds image and weights to bf16 (bias stays fp32)
+        check_bf16(tc.grid_to_nchw(out.data, 28, 39), F.relu(F.conv2d(bf(xs).double(), bf(ws).double(), bs.double())), "stem")
+        fma = tc.stem_conv3x3(xs.cuda(), ws.cuda(), bs.cuda(), fma=True)     # fp32 CUDA-core version of the same layer
+        check_bf16(tc.grid_to_nchw(fma.data, 28, 39), F.relu(F.conv2d(xs, ws, bs)), "stem fma")
+        d = (tc.grid_to_nchw(out.data, 28, 39) - tc.grid_to_nchw(fma.data, 28, 39)).abs().max().item()
+        assert d <= 0.05, d
     # ConvLSTM cell update
     P, Ch = 204, 512
     gates, c = rnd(P, 4 * Ch, seed=5), rnd(P, Ch, seed=6)
@@ -224,6 +229,15 @@ def test_halo_conv_equals_reference_and_streaming_kernel(cuda_lib, N, H, W, vh, 
     finally:
         tc.USE_HALO = True
     assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()      # same math, different accumulation order
+
+
+@pytest.mark.parametrize("N,cin,H,W", [(1, 2, 260, 346), (3, 1, 17, 23), (5, 2, 3, 3), (2, 2, 64, 129)])
+def test_stem_tensor_core_matches_reference(cuda_lib, N, cin, H, W):
+    """learner_models.py OrigUNet unet_e11 + ReLU. Sizes cover partial last tiles and rows that straddle tiles."""
+    xs, ws, bs = rnd(N, cin, H, W, seed=12), rnd(32, cin, 3, 3, seed=13, scale=0.3), rnd(32, seed=14)
+    out = tc.stem_conv3x3(xs.cuda(), ws.cuda(), bs.cuda())
+    assert (out.vh, out.vw) == (H - 2, W - 2)
+    check_bf16(tc.grid_to_nchw(out.data, H - 2, W - 2), F.relu(F.conv2d(bf(xs).double(), bf(ws).double(), bs.double())), "stem tc")
 
 
 @pytest.mark.parametrize("N,vh,vw,Cin,Cout", [(2, 20, 24, 32, 32), (1, 37, 29, 64, 64), (3, 19, 13, 32, 64), (1, 71, 150, 64, 128), (1, 4, 4, 32, 32)])
