@@ -195,7 +195,8 @@ class PipelineWorkload:
         self.h2d_bytes = sum(p.numel() for p in self.pinned_list)
         self.d2h_bytes = self.N_TRAJ * self.T * 3 * 4
         self.windows_per_step = self.N_TRAJ * self.T
-        # work of the tcgen05 kernels: UNet convs (minus the CUDA-core stem) + ConvLSTM + the ViT Linear layers
+        # work of the tcgen05 conv/GEMM kernels: UNet convs (minus the stem, which has its own small-K, HBM-bound
+        # tensor-core kernel and is not timed here) + ConvLSTM + the ViT Linear layers
         # (q/kv/final/mlp1/mlp2 = 54.0 MFLOP/frame of the 0.1106 G ViT-LSTM total) + decoder Linear 4.7 M
         W_ = self.N_TRAJ * self.T
         self.tc_flops = W_ * (self.FLOP_UNET - self.FLOP_STEM + self.FLOP_CONVLSTM + 0.0587e9)
@@ -234,7 +235,8 @@ class PipelineWorkload:
         from evfly_b200 import tc
         torch = self.torch
         self._ev = getattr(self, "_ev", [])
-        orig, orig_halo, orig_scan = tc._call, tc._call_halo, tc._call_scan
+        hooks = ("_call", "_call_halo", "_call_halo_pool", "_call_scan")       # every launcher of the tcgen05 conv/GEMM kernels
+        orig = {h: getattr(tc, h) for h in hooks}
 
         def timed(fn):
             def wrapper(*a):
@@ -242,7 +244,8 @@ class PipelineWorkload:
                 e0.record(); fn(*a); e1.record()
                 self._ev.append((e0, e1))
             return wrapper
-        tc._call, tc._call_halo, tc._call_scan = timed(orig), timed(orig_halo), timed(orig_scan)
+        for h in hooks:
+            setattr(tc, h, timed(orig[h]))
         try:
             with torch.no_grad():
                 self.pipe.reset()
@@ -259,7 +262,8 @@ class PipelineWorkload:
                     dv = torch.full((T * n, 1), 4.0, dtype=torch.float32, device=self.dev)
                     self.model.forward_trajectories([tm, dv, [None, None], None], n)
         finally:
-            tc._call, tc._call_halo, tc._call_scan = orig, orig_halo, orig_scan
+            for h in hooks:
+                setattr(tc, h, orig[h])
 
     def check(self):
         """one short sequence against the oracle (bf16 tolerance, tests/test_models_bf16_gpu.py)"""
@@ -285,7 +289,9 @@ class PipelineWorkload:
         torch.cuda.synchronize()
         n_steps = max(1, len(self._acc_ev))
         tc_ms = sum(a.elapsed_time(b) for a, b in self._ev)
-        launches = len(self._ev) / n_steps + (self.T - 1)      # the ConvLSTM scan is one timed call of T launches
+        from evfly_b200 import tc
+        # the ConvLSTM scan is one timed call: one persistent launch, or T step launches
+        launches = len(self._ev) / n_steps + (0 if tc.PERSISTENT_SCAN else self.T - 1)
         ach = self.tc_flops / (tc_ms / n_steps / 1e3) / 1e12
         acc_ms = sum(a.elapsed_time(b) for a, b in self._acc_ev) / n_steps
         self._extra = {"rooflines_other": [{
@@ -326,7 +332,7 @@ class PipelineWorkload:
 
     # ---- CPU port of the reference algorithm (oracle/) on a bounded sample --------------------------
     CPU_T = 8
-    cpu_sample = "1 trajectory of 8 windows (of the step's 256): C accumulation loop + numpy quantile + torch-CPU fp32 forward, all host threads"
+    cpu_sample = "1 trajectory of 8 windows (a slice of the step's windows): C accumulation loop + numpy quantile + torch-CPU fp32 forward, all host threads"
 
     @classmethod
     def cpu_only(cls, rank):
