@@ -15,7 +15,10 @@ from .events import L1
 
 
 class PerceptionPipeline:
-    def __init__(self, model, sensor_hw=(480, 640), model_hw=(260, 346), num_bins=5, desvel=4.0, device=None):
+    def __init__(self, model, sensor_hw=(480, 640), model_hw=(260, 346), num_bins=5, desvel=4.0, device=None, aligner=None):
+        """aligner: optional evfly_b200.calibration_tools.Aligner -- the event frame is rectified (cv2.remap bicubic)
+        between decode and centre crop like evfly_ros/run.py:339-340 (--align_evframe)."""
+        self.aligner = aligner
         self.model = model
         self.H, self.W = sensor_hw
         self.h, self.w = model_hw
@@ -40,8 +43,18 @@ class PerceptionPipeline:
                                               sorted_by_time=sorted_by_time)
         frames = torch.empty((T, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
         st = _lib.stream_ptr()
-        _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), T, self.H, self.W, self.h, self.w, 0.2,
-                                         _lib.ptr(frames), st), "evfly_decode_crop")
+        if self.aligner is None:
+            _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), T, self.H, self.W, self.h, self.w, 0.2,
+                                             _lib.ptr(frames), st), "evfly_decode_crop")
+        else:
+            # run.py:334-351: decode at full resolution, rectify, then centre-crop; only the cropped window of the
+            # remap is computed (the maps are indexed by OUTPUT pixel)
+            from .calibration_tools import remap_bicubic
+            full = torch.empty((T, self.H, self.W), dtype=torch.float32, device=self.dev)
+            _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), T, self.H, self.W, self.H, self.W, 0.2,
+                                             _lib.ptr(full), st), "evfly_decode_crop")
+            mx, my = self.aligner.davis_window(self.h, self.w)
+            remap_bicubic(full, mx, my, out=frames.view(T, self.h, self.w))
         _lib.check(lib.evfly_quantile_scale_clip(_lib.ptr(frames), T, self.h * self.w, 0.97, -1.0, 1.0, 0.0,
                                                  _lib.ptr(frames), None, st), "evfly_quantile_scale_clip")
         return frames, counts, voxel

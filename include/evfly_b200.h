@@ -209,6 +209,23 @@ int evfly_difflog_events_f64(const double* d_im, const double* d_prev, int64_t n
  * evfly_quantile_scale_clip.                                                                       */
 int evfly_min_cutoff_f32(float* d_x, int64_t n, float cutoff, void* stream);
 
+/* ---- next row N3: rectification (utils/calibration_tools/rectify_bag.py:91-138; evfly_ros/run.py:339-340) ----
+ * dst[n][i][j] = cv2.remap(src[n], mapx, mapy, INTER_CUBIC) (constant-0 border), bit for bit: coordinates rounded
+ * half-even to 1/32 pixel, A = -0.75 cubic table, OpenCV's summation order, no FMA. src: float32 [N,H,W], or with
+ * src_is_u8 the accumulator's byte image decoded on the fly as (v - 128) * 0.2 (run.py:334-336). The maps
+ * [OH rows of OW, row pitch map_ld floats] are shared by the N images; passing a window of the maps computes only
+ * that window of the output (e.g. the 260x346 centre crop of run.py:346-351). flip: img[:, ::-1] before the remap;
+ * rotate: cv2.rotate(ROTATE_180) of the result (remap_img's arguments).                                       */
+int evfly_remap_bicubic_f32(const void* d_src, int src_is_u8, int N, int H, int W, const float* d_mapx,
+                            const float* d_mapy, int64_t map_ld, int OH, int OW, int flip, int rotate, float* d_dst,
+                            void* stream);
+
+/* remap_events (rectify_bag.py:101-116): out_x = mapx[y][x], out_y = mapy[y][x] (maps [H,W]), optional rotation
+ * about (target_w-1, target_h-1), keep[i] = 1 when the result lies inside [0, target-1]; the caller compacts. */
+int evfly_remap_events_f32(const int32_t* d_x, const int32_t* d_y, int64_t n, const float* d_mapx,
+                           const float* d_mapy, int H, int W, int rotate, int target_w, int target_h,
+                           float* d_out_x, float* d_out_y, uint8_t* d_keep, void* stream);
+
 /* ======================================================================================
  * L3  model forward: operator entry points (fp32 exact path)
  *

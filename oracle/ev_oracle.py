@@ -246,3 +246,79 @@ def normalize_event_frames(ev, rescale_evs=-1.0, evs_min_cutoff=None):
     if evs_min_cutoff is not None:
         ev[ev.abs() < evs_min_cutoff] = 0.0
     return ev.numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row N3: event-frame / depth rectification (utils/calibration_tools/rectify_bag.py:91-138,
+# evfly_ros/run.py:339-340). The arithmetic lives in a third-party dependency, OpenCV's cv2.remap (4.13 in this
+# image; imgproc/src/imgwarp.cpp: remap() fixed-point map conversion + remapBicubic<Cast<float,float>,float,1>,
+# BORDER_CONSTANT 0); restated below and pinned bit-for-bit against cv2.remap and against the reference's own
+# Aligner run on its shipped calibration (tests/golden/make_golden_remap.py).
+# ---------------------------------------------------------------------------------------------
+def cubic_table() -> np.ndarray:
+    """OpenCV interpolateCubic (A = -0.75) at x = i/32, float32 [32][4]; every entry is exact in float32."""
+    f32 = np.float32
+    A = f32(-0.75)
+    tab = np.zeros((32, 4), f32)
+    for i in range(32):
+        x = f32(i) * f32(1.0 / 32)
+        x1, y = x + f32(1), f32(1) - x
+        tab[i, 0] = ((A * x1 - f32(5) * A) * x1 + f32(8) * A) * x1 - f32(4) * A
+        tab[i, 1] = ((A + f32(2)) * x - (A + f32(3))) * x * x + f32(1)
+        tab[i, 2] = ((A + f32(2)) * y - (A + f32(3))) * y * y + f32(1)
+        tab[i, 3] = f32(1) - tab[i, 0] - tab[i, 1] - tab[i, 2]
+    return tab
+
+
+def remap_bicubic(src, mapx, mapy) -> np.ndarray:
+    """cv2.remap(src float32 [H,W], mapx, mapy float32 [OH,OW], INTER_CUBIC) with the default constant-0 border.
+    Coordinates are rounded to 1/32 pixel (round-half-even of map*32), the 16 weights are float32 products of the
+    two 1-D table rows; interior pixels sum row by row (((a+b)+c)+d per row, rows added in order), pixels whose
+    4x4 window leaves the image accumulate the in-range taps one by one from 0. No fused multiply-add."""
+    f32 = np.float32
+    src = np.ascontiguousarray(src, dtype=f32)
+    H, W = src.shape
+    mapx, mapy = np.asarray(mapx, dtype=f32), np.asarray(mapy, dtype=f32)
+    tab = cubic_table()
+    sx = np.rint(mapx * f32(32)).astype(np.int64)
+    sy = np.rint(mapy * f32(32)).astype(np.int64)
+    fx, fy = sx & 31, sy & 31
+    ix = np.clip(sx >> 5, -32768, 32767) - 1
+    iy = np.clip(sy >> 5, -32768, 32767) - 1
+    wx, wy = tab[fx], tab[fy]                                   # [...,4]
+    interior = (ix >= 0) & (ix < max(W - 3, 0)) & (iy >= 0) & (iy < max(H - 3, 0))
+    fast = None
+    slow = np.zeros(mapx.shape, f32)
+    for k1 in range(4):
+        yy = iy + k1
+        yok = (yy >= 0) & (yy < H)
+        row = None
+        for k2 in range(4):
+            xx = ix + k2
+            ok = yok & (xx >= 0) & (xx < W)
+            v = np.where(ok, src[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], f32(0))
+            term = (v * (wy[..., k1] * wx[..., k2]).astype(f32)).astype(f32)
+            row = term if row is None else (row + term).astype(f32)
+            slow = np.where(ok, (slow + term).astype(f32), slow)
+        fast = row if fast is None else (fast + row).astype(f32)
+    return np.where(interior, fast, slow).astype(f32)
+
+
+def remap_img(img, maps, flip=False, rotate=False) -> np.ndarray:
+    """rectify_bag.py:91-98."""
+    img = np.asarray(img, dtype=np.float32)
+    if flip:
+        img = img[:, ::-1]
+    out = remap_bicubic(img, maps[0], maps[1])
+    return out[::-1, ::-1].copy() if rotate else out          # cv2.rotate(ROTATE_180)
+
+
+def remap_events(events: dict, maps, rotate: bool, shape):
+    """rectify_bag.py:101-116: per-event lookup of the inverse maps + in-frame mask (coordinates stay float)."""
+    mx, my = maps
+    x, y = mx[events["y"], events["x"]], my[events["y"], events["x"]]
+    tw, th = shape
+    if rotate:
+        x, y = tw - 1 - x, th - 1 - y
+    m = (x >= 0) & (x <= tw - 1) & (y >= 0) & (y <= th - 1)
+    return {"x": x[m], "y": y[m], "t": events["t"][m], "p": events["p"][m]}

@@ -167,3 +167,33 @@ def test_quantile_scale_clip_matches_torch_pipeline():
         ref[ref.abs() < 1e-3] = 0.0                       # learner_models.py:477
         assert np.array_equal(out[i:i + 1], ref.numpy(), equal_nan=True)
     assert np.isnan(out[2]).all()
+
+
+# ---- row N3: the remap oracle vs the reference's Aligner (golden) and vs cv2 when it is importable ---------
+def test_remap_oracle_matches_reference_golden(golden_dir):
+    G = np.load(os.path.join(golden_dir, "remap_golden.npz"))
+    ev = G["u8"].astype(np.float32)
+    ev -= 128
+    ev *= 0.2
+    for k in ("tl", "mid", "br"):
+        assert np.array_equal(O.remap_bicubic(ev, G[f"{k}_mapx"], G[f"{k}_mapy"]), G[f"{k}_out"]), k
+    H, W = (int(v) for v in G["shape"])
+    mx, my = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+    mx[:64, :64], my[:64, :64] = G["inv_mapx_win"], G["inv_mapy_win"]
+    evs = {k: G[f"ev_in_{k}"] for k in ("x", "y", "t", "p")}
+    for rot in (0, 1):
+        got = O.remap_events(evs, (mx, my), bool(rot), (W, H))
+        for k in ("x", "y", "t", "p"):
+            assert np.array_equal(got[k], G[f"ev_rot{rot}_{k}"]), (rot, k)
+
+
+def test_remap_oracle_matches_cv2_bit_for_bit():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    for (H, W, OH, OW) in [(40, 56, 37, 45), (120, 160, 120, 160), (5, 7, 9, 11), (3, 3, 8, 8)]:
+        src = rng.normal(0, 3, (H, W)).astype(np.float32)
+        mx = (rng.random((OH, OW)) * (W + 10) - 5).astype(np.float32)
+        my = (rng.random((OH, OW)) * (H + 10) - 5).astype(np.float32)
+        assert np.array_equal(O.remap_bicubic(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_CUBIC))
+        assert np.array_equal(O.remap_img(src, (mx, my), True, True),
+                              cv2.rotate(cv2.remap(np.ascontiguousarray(src[:, ::-1]), mx, my, cv2.INTER_CUBIC), cv2.ROTATE_180))
