@@ -35,3 +35,16 @@ def normalize_event_frames(ev, rescale_evs: float = -1.0, evs_min_cutoff=None) -
         if cutoff > 0:
             _lib.check(lib.evfly_min_cutoff_f32(_lib.ptr(out), out.numel(), cutoff, _lib.stream_ptr()), "evfly_min_cutoff_f32")
     return out
+
+
+def resize_trajectory(x, resize_input) -> torch.Tensor:
+    """dataloading.py:401-416: F.interpolate(traj.unsqueeze(1), size=resize_input, mode='bilinear',
+    align_corners=False).squeeze() for one trajectory of images / depths / event frames [T,H,W] -> [T,h,w]
+    (float32 CUDA tensor). Same sampling positions and lerp order as torch (evfly_resize_bilinear_f32)."""
+    dev = _device()
+    x = torch.as_tensor(x).to(device=dev, dtype=torch.float32).contiguous()
+    T, H, W = x.shape
+    h, w = resize_input
+    if (H, W) == (h, w):
+        return x
+    return ops.resize_bilinear(x.view(T, 1, H, W), (h, w), align_corners=False).view(T, h, w)

@@ -34,3 +34,16 @@ def test_difflog_events(cuda_lib):
                           O.difflog_events(np.log(im + 1e-5), np.log(prev + 1e-5), 0.15, 0.3, inputs_are_log=True))
     assert not compute_events(prev * 1.01, prev).any()
     assert compute_events(None, prev, shape=(60, 90)).shape == (60, 90)
+
+
+def test_resize_trajectory_matches_torch_interpolate(cuda_lib):
+    """dataloading.py:401-416 (resize_input): bilinear, align_corners=False, per trajectory."""
+    import torch.nn.functional as F
+    from evfly_b200.dataloading import resize_trajectory
+    g = torch.Generator().manual_seed(5)
+    for (T, H, W, size) in [(7, 260, 346, (60, 90)), (3, 480, 640, (260, 346)), (2, 60, 90, (60, 90)), (4, 33, 47, (64, 100))]:
+        x = torch.randn(T, H, W, generator=g)
+        want = F.interpolate(x.unsqueeze(1), size=size, mode="bilinear", align_corners=False).squeeze(1)
+        got = resize_trajectory(x.numpy(), size).cpu()
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)        # fp32 path tolerance (north_star)
