@@ -68,6 +68,7 @@ SIGNATURES.update({
     "evfly_linear_smallm_f32": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "evfly_pool2d_f32": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_resize_bilinear_f32": (_i32, [_vp, _p64, _vp, _p64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp]),
+    "evfly_resize_bilinear_premap_f32": (_i32, [_vp, _p64, _vp, _p64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp]),
     "evfly_layernorm_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
     "evfly_attention_small_f32": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_map4d_f32": (_i32, [_vp, _p64, _vp, _p64, _p64, _f32, _f32, _f32, _f32, _f32, _vp]),

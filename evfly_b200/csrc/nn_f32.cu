@@ -269,7 +269,8 @@ __device__ __forceinline__ void bilinear_src(int dst, int in, int out, bool alig
 
 __global__ void __launch_bounds__(256)
 k_resize_bilinear(const float* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W, int OH,
-                  int OW, int align, Strides4 xs, Strides4 ys, float mul, float add, float lo, float hi) {
+                  int OW, int align, Strides4 xs, Strides4 ys, float mul, float add, float lo, float hi,
+                  int pre, float pre_mul, float pre_lo, float pre_hi) {
     const long long total = (long long)N * C * OH * OW;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -281,8 +282,15 @@ k_resize_bilinear(const float* __restrict__ x, float* __restrict__ y, int N, int
         bilinear_src(oh, H, OH, align, h0, h1, lh);
         bilinear_src(ow, W, OW, align, w0, w1, lw);
         const float* p = x + n * xs.s[0] + c * xs.s[1];
-        const float v00 = p[h0 * xs.s[2] + w0 * xs.s[3]], v01 = p[h0 * xs.s[2] + w1 * xs.s[3]];
-        const float v10 = p[h1 * xs.s[2] + w0 * xs.s[3]], v11 = p[h1 * xs.s[2] + w1 * xs.s[3]];
+        float v00 = p[h0 * xs.s[2] + w0 * xs.s[3]], v01 = p[h0 * xs.s[2] + w1 * xs.s[3]];
+        float v10 = p[h1 * xs.s[2] + w0 * xs.s[3]], v11 = p[h1 * xs.s[2] + w1 * xs.s[3]];
+        if (pre) {      // the source is seen through clip(v * pre_mul, pre_lo, pre_hi) (NaN kept), without materialising it
+            v00 *= pre_mul; v01 *= pre_mul; v10 *= pre_mul; v11 *= pre_mul;
+            if (v00 == v00) v00 = fminf(fmaxf(v00, pre_lo), pre_hi);
+            if (v01 == v01) v01 = fminf(fmaxf(v01, pre_lo), pre_hi);
+            if (v10 == v10) v10 = fminf(fmaxf(v10, pre_lo), pre_hi);
+            if (v11 == v11) v11 = fminf(fmaxf(v11, pre_lo), pre_hi);
+        }
         float v = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
         v = v * mul + add;
         if (v == v) v = fminf(fmaxf(v, lo), hi);
@@ -588,7 +596,17 @@ extern "C" int evfly_resize_bilinear_f32(const float* d_x, const int64_t* xs, fl
     EVFLY_REQUIRE(d_x && d_y && xs && ys && N >= 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "resize_bilinear_f32: bad argument");
     if (N == 0) return EVFLY_OK;
     k_resize_bilinear<<<ew_grid((long long)N * C * OH * OW), 256, 0, (cudaStream_t)stream>>>(
-        d_x, d_y, N, C, H, W, OH, OW, align_corners, to_strides(xs), to_strides(ys), mul, add, lo, hi);
+        d_x, d_y, N, C, H, W, OH, OW, align_corners, to_strides(xs), to_strides(ys), mul, add, lo, hi, 0, 1.f, 0.f, 0.f);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_resize_bilinear_premap_f32(const float* d_x, const int64_t* xs, float* d_y, const int64_t* ys, int N, int C, int H, int W,
+                                               int OH, int OW, int align_corners, float pre_mul, float pre_lo, float pre_hi, void* stream) {
+    EVFLY_REQUIRE(d_x && d_y && xs && ys && N >= 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "resize_bilinear_premap_f32: bad argument");
+    if (N == 0) return EVFLY_OK;
+    k_resize_bilinear<<<ew_grid((long long)N * C * OH * OW), 256, 0, (cudaStream_t)stream>>>(
+        d_x, d_y, N, C, H, W, OH, OW, align_corners, to_strides(xs), to_strides(ys), 1.f, 0.f, -INFINITY, INFINITY, 1, pre_mul, pre_lo, pre_hi);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

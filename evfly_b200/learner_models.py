@@ -495,6 +495,11 @@ class OrigUNet_w_VITFLY_ViTLSTM(nn.Module):
         x = X[0]
         _, (x_depth, y_upconv, (h_unet, h_velpred)) = self.origunet.forward([x, None, X[2]], n_traj=n_traj)
         # * 2 roughly matches the depth scale VITFLY_ViTLSTM was trained on (:634)
-        x_depth_input = ops.map4d(x_depth, mul=2.0, lo=0.0, hi=1.0)
+        if tuple(x_depth.shape[-2:]) != (60, 90):
+            # vitfly's refine_inputs (vitfly_models.py:28-29) would resize the clamped depth to 60x90 next: do both in
+            # one pass over the four samples of each output pixel instead of materialising the full-size clamped image
+            x_depth_input = ops.resize_bilinear(x_depth, (60, 90), align_corners=False, pre=(2.0, 0.0, 1.0))
+        else:
+            x_depth_input = ops.map4d(x_depth, mul=2.0, lo=0.0, hi=1.0)
         x_vel, h_vitlstm = self.vitfly_vitlstm.forward([x_depth_input, X[1], None, X[3]], n_traj=n_traj)
         return x_vel, (x_depth, y_upconv, ((h_unet, h_velpred), h_vitlstm))

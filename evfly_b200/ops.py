@@ -86,7 +86,8 @@ def _s4(t):
     return (C.c_int64 * 4)(*t.stride())
 
 
-def resize_bilinear(x_view, size, align_corners=False, out_view=None, mul=1.0, add=0.0, lo=-INF, hi=INF):
+def resize_bilinear(x_view, size, align_corners=False, out_view=None, mul=1.0, add=0.0, lo=-INF, hi=INF, pre=None):
+    """pre=(mul, lo, hi): interpolate clip(x * mul, lo, hi) instead of x (fused, nothing materialised)."""
     lib = _lib.load()
     _f32(x_view, "resize_bilinear")
     N, Cc, H, W = x_view.shape
@@ -94,6 +95,12 @@ def resize_bilinear(x_view, size, align_corners=False, out_view=None, mul=1.0, a
     if out_view is None:
         out_view = torch.empty((N, Cc, OH, OW), dtype=torch.float32, device=x_view.device)
     assert tuple(out_view.shape) == (N, Cc, OH, OW)
+    if pre is not None:
+        assert (mul, add, lo, hi) == (1.0, 0.0, -INF, INF)
+        _lib.check(lib.evfly_resize_bilinear_premap_f32(x_view.data_ptr(), _s4(x_view), out_view.data_ptr(), _s4(out_view), N, Cc, H, W,
+                                                        OH, OW, int(align_corners), float(pre[0]), float(pre[1]), float(pre[2]),
+                                                        _lib.stream_ptr()), "evfly_resize_bilinear_premap_f32")
+        return out_view
     _lib.check(lib.evfly_resize_bilinear_f32(x_view.data_ptr(), _s4(x_view), out_view.data_ptr(), _s4(out_view), N, Cc, H, W,
                                              OH, OW, int(align_corners), mul, add, lo, hi, _lib.stream_ptr()),
                "evfly_resize_bilinear_f32")

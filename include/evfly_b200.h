@@ -285,6 +285,13 @@ int evfly_resize_bilinear_f32(const float* d_x, const int64_t* xs, float* d_y, c
                               int N, int C, int H, int W, int OH, int OW, int align_corners,
                               float mul, float add, float lo, float hi, void* stream);
 
+/* resize_bilinear(clip(x * pre_mul, pre_lo, pre_hi)) without materialising the clipped tensor: the glue between
+ * the depth UNet and the ViT (learner_models.py:634 `x_depth * 2` clamped to [0,1], then vitfly_models.py:28-29
+ * resize to 60x90). Same values as the two-step form (the map is applied to the four samples).              */
+int evfly_resize_bilinear_premap_f32(const float* d_x, const int64_t* xs, float* d_y, const int64_t* ys, int N,
+                                     int C, int H, int W, int OH, int OW, int align_corners, float pre_mul,
+                                     float pre_lo, float pre_hi, void* stream);
+
 /* nn.LayerNorm over the last dimension of contiguous [rows, C] (C <= 1024), eps inside sqrt. */
 int evfly_layernorm_f32(const float* d_x, const float* d_gamma, const float* d_beta, float* d_y,
                         int64_t rows, int C, float eps, void* stream);

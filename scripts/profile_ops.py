@@ -16,6 +16,7 @@ torch.cuda.synchronize()
 lib = _lib.load()
 records = collections.defaultdict(list)
 shapes = collections.defaultdict(list)
+order = []
 orig = {}
 for fn in _lib.SIGNATURES:
     if fn in ("evfly_last_error", "evfly_abi_version", "evfly_launch_count") or fn.endswith("_bytes"):
@@ -27,6 +28,7 @@ for fn in _lib.SIGNATURES:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); rc = f(*a); e1.record()
             records[fn].append((e0, e1))
+            order.append((fn, e0, e1))
             if fn == "evfly_tc_conv_bf16":       # per-shape breakdown of the GEMM family
                 st = a[0]._obj if hasattr(a[0], "_obj") else a[0].contents
                 shapes[(st.M_rows, st.Cin, st.n_rows, st.taps, st.convt, st.Hp, st.Wp)].append((e0, e1))
@@ -49,3 +51,8 @@ for k, v in sorted(shapes.items(), key=lambda kv: -sum(x.elapsed_time(y) for x, 
     M, Cin, n_rows, taps = k[0], k[1], k[2], k[3]
     tf = 2.0 * M * Cin * taps * n_rows * len(v) / ms / 1e9
     print(f"{ms:8.3f} ms {len(v):3d} calls {tf:7.1f} TFLOP/s  {k}")
+
+if "--each" in sys.argv:
+    print("every call in launch order (ms):")
+    for fn, e0, e1 in order:
+        print(f"{e0.elapsed_time(e1):8.3f}  {fn}")

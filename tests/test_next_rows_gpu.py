@@ -38,6 +38,7 @@ def test_difflog_events(cuda_lib):
 
 def test_resize_trajectory_matches_torch_interpolate(cuda_lib):
     """dataloading.py:401-416 (resize_input): bilinear, align_corners=False, per trajectory."""
+    import torch
     import torch.nn.functional as F
     from evfly_b200.dataloading import resize_trajectory
     g = torch.Generator().manual_seed(5)
