@@ -145,7 +145,8 @@ def test_layernorm_attention_dwconv_bf16(cuda_lib):
         att = torch.softmax(qr @ kvr[0].transpose(-2, -1) / d ** 0.5, dim=-1)
         want = (att @ kvr[1]).transpose(1, 2).reshape(B, N, C)
         check_bf16(tc.attention_small_bf16(q.to(BF).cuda(), kv.to(BF).cuda(), heads), want, "attention")
-    for B, H, W, C in [(2, 15, 23, 32), (2, 8, 12, 64)]:
+    # the last three shapes take the 4-pixels-per-thread kernel (>= 4096 pixels), incl. a row width that is not a multiple of 4
+    for B, H, W, C in [(2, 15, 23, 32), (2, 8, 12, 64), (16, 15, 23, 32), (48, 8, 12, 64), (5, 30, 37, 16)]:
         Ce = 8 * C
         x = bf(rnd(B, H, W, Ce, seed=1))
         w, b = rnd(Ce, 8, 3, 3, seed=2, scale=72 ** -0.5), rnd(Ce, seed=3)
