@@ -24,6 +24,7 @@ struct HaloArgs {
     __nv_bfloat16* out;   // [N, Hp, Wp, COUT], same pitch as the input
     __nv_bfloat16* pool_out;   // optional fused MaxPool2d(2): [N, Hp2, Wp2, COUT], valid (out_vh/2) x (out_vw/2)
     int Hp2, Wp2;
+    int pad;              // 1: padding=1 conv on a dense tensor (Hp x Wp all valid): the halo box starts at (-1,-1) and TMA zero-fills outside the image
     int N, Hp, Wp, out_vh, out_vw;
     int tiles_x, tiles_y;
     int relu;
@@ -118,7 +119,7 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], Cfg::HALO_ROWS * Cfg::ROW_B);
-            tma_load_4d(s_halo + stage * Cfg::HALO_BYTES, &map_x, &full_bar[stage], 0, tx * 8, ty * 16, n);
+            tma_load_4d(s_halo + stage * Cfg::HALO_BYTES, &map_x, &full_bar[stage], 0, tx * 8 - p.pad, ty * 16 - p.pad, n);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
@@ -280,7 +281,7 @@ static int launch_halo(const void* x, const void* w, const HaloArgs& p, cudaStre
 using namespace evfly;
 
 static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp, int Wp,
-                     int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream) {
+                     int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream, int pad = 0) {
     EVFLY_REQUIRE(d_x && d_w && d_out && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
     EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128),
                   "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64} or (64,128) (got %d, %d)", Cin, Cout);
@@ -290,8 +291,9 @@ static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void
     p.N = N;
     p.Hp = Hp;
     p.Wp = Wp;
-    p.out_vh = vh - 2;
-    p.out_vw = vw - 2;
+    p.pad = pad;
+    p.out_vh = vh - 2 + 2 * pad;
+    p.out_vw = vw - 2 + 2 * pad;
     p.tiles_x = (p.out_vw + 7) / 8;
     p.tiles_y = (p.out_vh + 15) / 16;
     p.relu = relu;
@@ -317,4 +319,9 @@ extern "C" int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w,
                                                int Wp, int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream) {
     EVFLY_REQUIRE(d_pool, "tc_conv3x3_halo_pool_bf16: null pool output");
     return halo_conv(d_x, d_w, d_bias, d_out, d_pool, N, Hp, Wp, vh, vw, Cin, Cout, relu, Hp2, Wp2, stream);
+}
+
+extern "C" int evfly_tc_conv3x3_same_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int H, int W, int Cin,
+                                          int Cout, int relu, void* stream) {
+    return halo_conv(d_x, d_w, d_bias, d_out, nullptr, N, H, W, H, W, Cin, Cout, relu, 0, 0, stream, 1);
 }

@@ -307,6 +307,65 @@ k_dwconv3x3_gelu(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
     *reinterpret_cast<uint4*>(y + pix * Ce + g * 8) = o;
 }
 
+// ---------------------------------------------------------------------------------------
+// Tail of the ViT encoder (vitfly_models.py:136-142): cat([PixelShuffle(2)(s2), Upsample((2*H2, 2*W2), bilinear,
+// align_corners=True)(s1)], dim=1) written as ONE dense NHWC bf16 tensor [B, 2*H2, 2*W2, ld] (channels
+// [0, C2/4) shuffle, [C2/4, C2/4+C1) upsample, the rest zero) that the tensor-core 3x3 conv reads directly.
+// One thread per (pixel, 8-channel chunk).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilin_src_align(int dst, int in, int out, int& i0, int& i1, float& l1) {
+    const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    const float src = scale * (float)dst;
+    i0 = (int)src;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+k_shuffle_upsample_cat(const __nv_bfloat16* __restrict__ t2, int H2, int W2, int C2, const __nv_bfloat16* __restrict__ t1, int H1, int W1,
+                       int C1, __nv_bfloat16* __restrict__ out, long long B, int ld) {
+    const int OH = 2 * H2, OW = 2 * W2, chunks = ld >> 3, cs = C2 >> 2;
+    const long long total = B * OH * OW * chunks;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ch = (int)(i % chunks);
+    const long long pix = i / chunks;
+    const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH);
+    const long long b = pix / ((long long)OW * OH);
+    const int c0 = ch * 8;
+    float f[8];
+    if (c0 < cs) {                     // PixelShuffle: out[c][2h+i][2w+j] = in[4c + 2i + j][h][w]
+        const __nv_bfloat16* src = t2 + ((b * H2 + (oy >> 1)) * W2 + (ox >> 1)) * C2 + (oy & 1) * 2 + (ox & 1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = c0 + e < cs ? __bfloat162float(src[(c0 + e) * 4]) : 0.f;
+    } else if (c0 < cs + C1) {         // bilinear, align_corners=True
+        int h0, h1, w0, w1;
+        float lh, lw;
+        bilin_src_align(oy, H1, OH, h0, h1, lh);
+        bilin_src_align(ox, W1, OW, w0, w1, lw);
+        const __nv_bfloat16* base = t1 + b * (long long)H1 * W1 * C1 + (c0 - cs);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (c0 - cs + e < C1) {
+                const float v00 = __bfloat162float(base[((long long)h0 * W1 + w0) * C1 + e]), v01 = __bfloat162float(base[((long long)h0 * W1 + w1) * C1 + e]);
+                const float v10 = __bfloat162float(base[((long long)h1 * W1 + w0) * C1 + e]), v11 = __bfloat162float(base[((long long)h1 * W1 + w1) * C1 + e]);
+                f[e] = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+            } else {
+                f[e] = 0.f;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    }
+    uint4 o;
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) po[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    *reinterpret_cast<uint4*>(out + pix * ld + c0) = o;
+}
+
 // Same op, 4 horizontally adjacent pixels per thread: the 576 weights of the group are read from shared memory
 // once per 4 pixels (LDS:FMA 1:16 instead of 1:4 -- the 1-pixel version is shared-memory-issue bound) and the
 // 3 x 6 input window is loaded once (18 loads instead of 36).
@@ -541,6 +600,19 @@ extern "C" int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, 
     const int threads = ((4 * H + 31) / 32) * 32;
     k_lstm_seq_smemw<<<n_seq, threads, smem, (cudaStream_t)stream>>>(d_gx, reinterpret_cast<const __nv_bfloat162*>(d_whh_pairs), d_h0, d_c0,
                                                                      d_hs, d_hT, d_cT, T, H, n_seq);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_shuffle_upsample_cat_bf16(const void* d_t2, int H2, int W2, int C2, const void* d_t1, int H1, int W1, int C1, void* d_out,
+                                               int64_t B, int ld, void* stream) {
+    EVFLY_REQUIRE(d_t2 && d_t1 && d_out && B >= 0 && H2 > 0 && W2 > 0 && H1 > 0 && W1 > 0 && C2 % 32 == 0 && C1 % 8 == 0 && ld % 8 == 0 && ld >= C2 / 4 + C1,
+                  "shuffle_upsample_cat_bf16: bad argument (C2 % 32 == 0, C1 % 8 == 0, ld >= C2/4 + C1)");
+    if (B == 0) return EVFLY_OK;
+    const long long total = B * 4 * H2 * W2 * (ld / 8);
+    k_shuffle_upsample_cat<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d_t2), H2, W2, C2, reinterpret_cast<const __nv_bfloat16*>(d_t1), H1, W1, C1,
+        reinterpret_cast<__nv_bfloat16*>(d_out), B, ld);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

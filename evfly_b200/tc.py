@@ -88,6 +88,27 @@ def conv3x3_pool(g: Grid, w_packed, bias, relu=True):
     return out, pooled
 
 
+def conv3x3_same(x_nhwc: torch.Tensor, w_packed, bias, relu=False) -> torch.Tensor:
+    """Conv2d(k=3, padding=1) on a dense bf16 NHWC tensor [N,H,W,Cin] (Cin in {32,64}) -> [N,H,W,Cout]."""
+    N, H, W, Cin = x_nhwc.shape
+    Cout = w_packed.shape[0]
+    assert x_nhwc.is_contiguous() and x_nhwc.dtype == BF16
+    out = torch.empty((N, H, W, Cout), dtype=BF16, device=x_nhwc.device)
+    _lib.check(_lib.load().evfly_tc_conv3x3_same_bf16(x_nhwc.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data_ptr(), N, H, W, Cin, Cout,
+                                                       int(relu), _lib.stream_ptr()), "evfly_tc_conv3x3_same_bf16")
+    return out
+
+
+def shuffle_upsample_cat(t2, H2, W2, t1, H1, W1, ld) -> torch.Tensor:
+    """cat([PixelShuffle(2)(t2), Upsample((2*H2,2*W2), align_corners=True)(t1)]) as bf16 NHWC [B,2*H2,2*W2,ld] (zero-padded channels)."""
+    B = t2.shape[0]
+    C2, C1 = t2.shape[-1], t1.shape[-1]
+    out = torch.empty((B, 2 * H2, 2 * W2, ld), dtype=BF16, device=t2.device)
+    _lib.check(_lib.load().evfly_shuffle_upsample_cat_bf16(t2.data_ptr(), H2, W2, C2, t1.data_ptr(), H1, W1, C1, out.data_ptr(), B, ld,
+                                                            _lib.stream_ptr()), "evfly_shuffle_upsample_cat_bf16")
+    return out
+
+
 def _call(a: _lib.TcConvArgs):
     _lib.check(_lib.load().evfly_tc_conv_bf16(C.byref(a), _lib.stream_ptr()), "evfly_tc_conv_bf16")
 

@@ -85,6 +85,32 @@ class _ViTEncoder(PackedModule):
         return ops.conv2d(cat, ds.weight, ds.bias, pad=1).view(N, -1)
 
 
+    TAIL_CIN, TAIL_COUT = 64, 32      # down_sample's 48 -> 12 channels zero-padded to what the halo conv kernel takes
+
+    def _pack_tail_tc(self, decoder_weight):
+        """Weights of the tensor-core tail: down_sample as [32, 9*64] bf16 and the decoder Linear re-indexed from the
+        reference's NCHW flatten (c*384 + y*24 + x, vitfly_models.py:142) to the NHWC-padded order (y*24 + x)*32 + c."""
+        ds = self.down_sample
+        w = torch.zeros((self.TAIL_COUT, self.TAIL_CIN, 3, 3), dtype=torch.float32, device=ds.weight.device)
+        w[:12, :48] = ds.weight
+        b = torch.zeros((self.TAIL_COUT,), dtype=torch.float32, device=ds.weight.device)
+        b[:12] = ds.bias
+        n_out = decoder_weight.shape[0]
+        dec = torch.zeros((n_out, 16, 24, self.TAIL_COUT), dtype=torch.float32, device=decoder_weight.device)
+        dec[..., :12] = decoder_weight.view(n_out, 12, 16, 24).permute(0, 2, 3, 1)
+        return {"ds_w": tc.pack_conv3x3_weight(w), "ds_b": b, "dec": dec.view(n_out, -1).to(tc.BF16).contiguous()}
+
+    def _encode_tc(self, depth, tail):
+        """bf16 path for batches: [N,1,60,90] -> bf16 features [N, 16*24*32] in NHWC-padded order (see _pack_tail_tc);
+        everything after the token stages stays bf16 NHWC and on the tensor cores."""
+        N = depth.shape[0]
+        b0, b1 = self.encoder_blocks
+        t1, H1, W1 = b0.encode_bf16(depth.contiguous(), True, N, depth.shape[2], depth.shape[3])
+        t2, H2, W2 = b1.encode_bf16(t1, False, N, H1, W1)
+        cat = tc.shuffle_upsample_cat(t2, H2, W2, t1, H1, W1, self.TAIL_CIN)          # [N,16,24,64]
+        return tc.conv3x3_same(cat, tail["ds_w"], tail["ds_b"]).view(N, -1)
+
+
 class LSTMNetVIT(_ViTEncoder):
     """
     ViT+LSTM Network
@@ -101,7 +127,7 @@ class LSTMNetVIT(_ViTEncoder):
 
     def _pack(self):
         dec = sn_effective_weight(self.decoder)
-        return {"decoder": dec, "decoder_bf16": dec.to(tc.BF16).contiguous(), "fc2": sn_effective_weight(self.nn_fc2), "lstm": pack_lstm(self.lstm)}
+        return {"decoder": dec, "tail": self._pack_tail_tc(dec), "fc2": sn_effective_weight(self.nn_fc2), "lstm": pack_lstm(self.lstm)}
 
     def forward_trajectories(self, X, n_traj):
         """Extension: n_traj sequences advance together (rows time-major, state [3, n_traj, 128])."""
@@ -111,11 +137,13 @@ class LSTMNetVIT(_ViTEncoder):
         X = _inputs(self, X)
         pk = self.packed()
         N = X[0].shape[0]
-        feat = self._encode(X[0])
-        seq, feat_out = _meta_concat(512, [(X[1], 1.0, 10.0), (X[2], 1.0, 1.0)], N, feat.device)   # X[1]/10
-        if self.precision == 'bf16' and N >= 16:      # [N,4608] x [4608,512] on the tensor cores, fp32 out into the concat buffer
-            tc.gemm_into_f32(feat.to(tc.BF16), pk["decoder_bf16"], self.decoder.bias, seq, 0)
+        seq, feat_out = _meta_concat(512, [(X[1], 1.0, 10.0), (X[2], 1.0, 1.0)], N, X[0].device)   # X[1]/10
+        if self.precision == 'bf16' and N >= 16:
+            # batches: tail + decoder Linear on the tensor cores, fp32 out into the concat buffer
+            feat = self._encode_tc(X[0], pk["tail"])
+            tc.gemm_into_f32(feat, pk["tail"]["dec"], self.decoder.bias, seq, 0)
         else:
+            feat = self._encode(X[0])
             ops.linear(feat, pk["decoder"], self.decoder.bias, out2d=feat_out)
         state = X[3] if len(X) > 3 else None
         out, h = run_lstm(ops, pk["lstm"], seq, state, 128, smem_weights=self.precision == 'bf16', n_seq=n_traj)

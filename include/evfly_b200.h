@@ -474,6 +474,18 @@ int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w, const floa
                                     int N, int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2,
                                     void* stream);
 
+/* 3x3 conv with padding=1 (+bias, +ReLU) on a DENSE bf16 NHWC tensor [N,H,W,Cin] -> [N,H,W,Cout] through the same
+ * halo-reuse kernel: the halo box starts at (-1,-1) and TMA zero-fills everything outside the image
+ * (vitfly_models.py:120 down_sample = Conv2d(48, 12, 3, padding=1), channels zero-padded to 64 / 32).   */
+int evfly_tc_conv3x3_same_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int H, int W,
+                               int Cin, int Cout, int relu, void* stream);
+
+/* vitfly_models.py:136-142: cat([PixelShuffle(2)(s2), Upsample((2*H2,2*W2), bilinear, align_corners=True)(s1)], 1)
+ * from the bf16 token tensors t2 [B,H2,W2,C2], t1 [B,H1,W1,C1] into one dense bf16 NHWC tensor
+ * [B,2*H2,2*W2,ld]: channels [0,C2/4) shuffle, [C2/4,C2/4+C1) upsample, [.., ld) zero.                 */
+int evfly_shuffle_upsample_cat_bf16(const void* d_t2, int H2, int W2, int C2, const void* d_t1, int H1, int W1,
+                                    int C1, void* d_out, int64_t B, int ld, void* stream);
+
 /* Hardware probe (diagnostic): D = x[shift : shift+128] @ w^T computed by tcgen05.mma from ONE TMA-loaded
  * [136, KC] tile whose descriptor starts `shift` rows into the swizzle atom (base-offset field set when
  * use_base_offset). x bf16 [136,KC], w bf16 [32,KC], out fp32 [128,32]. KC in {32 (64B swizzle), 64 (128B)}. */

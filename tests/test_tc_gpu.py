@@ -286,3 +286,31 @@ def test_persistent_convlstm_scan_equals_per_step_launches(cuda_lib, T, P, Ch):
         cc = torch.sigmoid(g[..., 1]) * cc + torch.sigmoid(g[..., 0]) * torch.tanh(g[..., 3])
         h = (torch.sigmoid(g[..., 2]) * torch.tanh(cc)).to(BF).double()
     check_bf16(outs[0][0][T], h, "scan h_T")
+
+
+def test_vit_tail_cat_and_same_padding_conv(cuda_lib):
+    """vitfly_models.py:136-142: cat([pxShuffle(s2), up_sample(s1)]) -> down_sample(k=3, padding=1), bf16 NHWC on the
+    tensor cores (channels zero-padded 48->64, 12->32) against torch fp64."""
+    B = 5
+    s1, s2 = bf(rnd(B, 32, 15, 23, seed=1)), bf(rnd(B, 64, 8, 12, seed=2))
+    w, b = rnd(12, 48, 3, 3, seed=3, scale=(9 * 48) ** -0.5), rnd(12, seed=4)
+    cat_ref = torch.cat([F.pixel_shuffle(s2.double(), 2), F.interpolate(s1.double(), size=(16, 24), mode="bilinear", align_corners=True)], dim=1)
+    t1 = s1.permute(0, 2, 3, 1).contiguous().to(BF).cuda()
+    t2 = s2.permute(0, 2, 3, 1).contiguous().to(BF).cuda()
+    cat = tc.shuffle_upsample_cat(t2, 8, 12, t1, 15, 23, 64)
+    assert cat.shape == (B, 16, 24, 64) and float(cat[..., 48:].abs().max()) == 0.0
+    check_bf16(cat[..., :48].permute(0, 3, 1, 2), cat_ref, "shuffle+upsample cat")
+    assert torch.equal(cat[..., :16].permute(0, 3, 1, 2).float().cpu(), F.pixel_shuffle(s2, 2))          # the shuffle is a pure copy
+    wp = torch.zeros(32, 64, 3, 3)
+    wp[:12, :48] = w
+    bp = torch.zeros(32)
+    bp[:12] = b
+    out = tc.conv3x3_same(cat, tc.pack_conv3x3_weight(wp.cuda()), bp.cuda())
+    want = F.conv2d(cat[..., :48].permute(0, 3, 1, 2).double().cpu(), bf(w).double(), b.double(), padding=1)
+    check_bf16(out[..., :12].permute(0, 3, 1, 2), want, "down_sample conv (padding=1)")
+    assert float(out[..., 12:].abs().max()) == 0.0
+    # a larger dense case for the same-padding conv, Cin = Cout = 64, odd extents, ReLU
+    x = bf(rnd(3, 64, 21, 35, seed=5))
+    w2, b2 = bf(rnd(64, 64, 3, 3, seed=6, scale=(9 * 64) ** -0.5)), rnd(64, seed=7)
+    got = tc.conv3x3_same(x.permute(0, 2, 3, 1).contiguous().to(BF).cuda(), tc.pack_conv3x3_weight(w2.cuda()), b2.cuda(), relu=True)
+    check_bf16(got.permute(0, 3, 1, 2), F.relu(F.conv2d(x.double(), w2.double(), b2.double(), padding=1)), "same conv 64->64")
