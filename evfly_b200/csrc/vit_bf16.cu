@@ -511,6 +511,10 @@ k_lstm_seq_smemw(const float* __restrict__ gx, const __nv_bfloat162* __restrict_
 
 }  // namespace evfly
 
+namespace evfly {
+int patch_embed_tc_dispatch(const void* x, int x_is_f32, const float* w, const float* bias, const float* gamma, const float* beta, void* out,
+                            long long tokens, int H, int W, int Cin, int Cout, int k, int s, int p, int OH, int OW, float eps, cudaStream_t st);
+}
 using namespace evfly;
 
 extern "C" int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, const float* d_w_kc, const float* d_bias,
@@ -523,6 +527,11 @@ extern "C" int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, con
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
     EVFLY_REQUIRE(OH > 0 && OW > 0, "patch_embed_ln_bf16: empty output");
     const long long total = (long long)B * OH * OW;
+    if (total >= 1024) {     // batches: im2col rows built in shared memory, GEMM on tcgen05, LayerNorm in the epilogue (tc_patch_embed.cu)
+        const int rc = patch_embed_tc_dispatch(d_x, x_is_f32_nchw, d_w_kc, d_bias, d_gamma, d_beta, d_tokens, total, H, W, Cin, Cout, k, stride, pad,
+                                               OH, OW, eps, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     const unsigned grid = (unsigned)ceil_div(total, 8);
     if (x_is_f32_nchw)
         k_patch_embed_ln<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(d_x), d_w_kc, d_bias, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_tokens), B, H, W, Cin, Cout, k, stride, pad, OH, OW, eps);

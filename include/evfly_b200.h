@@ -442,7 +442,10 @@ int evfly_nhwc_to_nchw_f32(const void* d_x, int src_is_f32, float* d_y, int N, i
 /* OverlapPatchMerging / the attention's reduction conv (ViTsubmodules.py:15-34, 43-44, 68-70):
  * conv(k, stride, pad) + bias + LayerNorm(Cout) fused, one warp per output token.
  * x: fp32 NCHW with Cin == 1 (x_is_f32_nchw) or bf16 NHWC [B,H,W,Cin]; w_kc fp32 [k*k*Cin][Cout]
- * with K index (kh*k + kw)*Cin + ci; tokens bf16 [B, OH*OW, Cout]; Cout in {32, 64}.           */
+ * with K index (kh*k + kw)*Cin + ci; tokens bf16 [B, OH*OW, Cout]; Cout in {32, 64}.
+ * From 1024 tokens up the two OverlapPatchMerging shapes (7x7/4 on the fp32 image, 3x3/2 on 32 channels) run on
+ * tcgen05: im2col rows built in swizzled shared memory by the token's thread, LayerNorm in the TMEM epilogue
+ * (evfly_b200/csrc/tc_patch_embed.cu); image and weights are rounded to bf16 there.                 */
 int evfly_patch_embed_ln_bf16(const void* d_x, int x_is_f32_nchw, const float* d_w_kc, const float* d_bias,
                               const float* d_gamma, const float* d_beta, void* d_tokens, int B, int H, int W,
                               int Cin, int Cout, int k, int stride, int pad, float eps, void* stream);

@@ -111,12 +111,13 @@ def test_nhwc_glue(cuda_lib):
 
 
 # ---- bf16 ViT kernels ---------------------------------------------------------------------------
-def test_patch_embed_ln_and_reduction_conv(cuda_lib):
-    B = 3
+@pytest.mark.parametrize("B", [2, 30])       # 30: >= 1024 tokens, the tensor-core kernels (operands rounded to bf16)
+def test_patch_embed_ln_and_reduction_conv(cuda_lib, B):
+    rt = bf if B >= 30 else (lambda t: t)
     # stage 1: fp32 depth image, 7x7 stride 4 pad 3, 1 -> 32, LayerNorm
     x = rnd(B, 1, 60, 90, seed=1)
     w, b, g, be = rnd(32, 1, 7, 7, seed=2, scale=0.15), rnd(32, seed=3), 1 + 0.1 * rnd(32, seed=4), 0.1 * rnd(32, seed=5)
-    y = F.conv2d(x, w, b, stride=4, padding=3)
+    y = F.conv2d(rt(x), rt(w), b, stride=4, padding=3)
     want = F.layer_norm(y.flatten(2).transpose(1, 2), (32,), g, be)
     tok, H, W = tc.patch_embed_ln(x.cuda(), True, tc.pack_conv_kc(w.cuda()), b.cuda(), g.cuda(), be.cuda(), B, 60, 90, 1, 32, 7, 4, 3, 1e-5)
     assert (H, W) == (15, 23)
@@ -126,7 +127,7 @@ def test_patch_embed_ln_and_reduction_conv(cuda_lib):
         xt = bf(rnd(B, Hh * Ww, Cin, seed=6))
         w, b = rnd(Cout, Cin, k, k, seed=7, scale=(Cin * k * k) ** -0.5), rnd(Cout, seed=8)
         g, be = 1 + 0.1 * rnd(Cout, seed=9), 0.1 * rnd(Cout, seed=10)
-        y = F.conv2d(xt.view(B, Hh, Ww, Cin).permute(0, 3, 1, 2), w, b, stride=s, padding=p)
+        y = F.conv2d(xt.view(B, Hh, Ww, Cin).permute(0, 3, 1, 2), rt(w) if k == 3 else w, b, stride=s, padding=p)
         want = F.layer_norm(y.flatten(2).transpose(1, 2), (Cout,), g, be)
         tok, H, W = tc.patch_embed_ln(xt.to(BF).cuda(), False, tc.pack_conv_kc(w.cuda()), b.cuda(), g.cuda(), be.cuda(), B, Hh, Ww, Cin, Cout, k, s, p, 1e-5)
         assert tok.shape == want.shape

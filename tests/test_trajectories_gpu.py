@@ -32,7 +32,9 @@ def test_batched_trajectories_equal_sequential(cuda_lib, precision):
             np.testing.assert_allclose(dep.view(T, n, 1, 260, 346)[:, s].cpu().numpy(), sdep.cpu().numpy(), **tol)
             np.testing.assert_allclose(hu[0][0][s].cpu().numpy(), shu[0][0][0].cpu().numpy(), **tol)
             np.testing.assert_allclose(hu[0][1][s].cpu().numpy(), shu[0][1][0].cpu().numpy(), **tol)
-            np.testing.assert_allclose(hv[0][:, s].cpu().numpy(), shv[0].cpu().numpy(), **tol)
+            # bf16: kernels are chosen by batch size (e.g. the patch embedding runs on the tensor cores from 1024 tokens
+            # up), so batched and sequential runs agree to bf16 noise, not bit for bit; the LSTM state gets a wider atol
+            np.testing.assert_allclose(hv[0][:, s].cpu().numpy(), shv[0].cpu().numpy(), **(tol if precision == "fp32" else dict(rtol=2e-2, atol=5e-2)))
         # carried state: a second chunk of the same trajectories continues where the first stopped
         frames2 = torch.stack([synthetic_frames(60 + s, T) for s in range(n)]).cuda()
         tm2 = frames2.transpose(0, 1).reshape(T * n, 1, 260, 346).contiguous()
