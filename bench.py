@@ -251,14 +251,16 @@ class PipelineWorkload:
                 self.pipe.reset()
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record()
-                fr = [self.pipe.frames_from_windows(d, self.d_edges)[0] for d in self.d_in_list]
+                if self.N_TRAJ == 1:
+                    fr = self.pipe.frames_from_windows(self.d_in_list[0], self.d_edges)[0]
+                else:
+                    tm = self.pipe.frames_from_trajectories(self.d_in_list, [self.d_edges] * self.N_TRAJ)[0]
                 a1.record()
                 self._acc_ev = getattr(self, "_acc_ev", []) + [(a0, a1)]
                 if self.N_TRAJ == 1:
-                    self.pipe.forward(fr[0])
+                    self.pipe.forward(fr)
                 else:
                     n, T = self.N_TRAJ, self.T
-                    tm = torch.stack(fr, dim=1).reshape(T * n, 1, self.H, self.W)
                     dv = torch.full((T * n, 1), 4.0, dtype=torch.float32, device=self.dev)
                     self.model.forward_trajectories([tm, dv, [None, None], None], n)
         finally:

@@ -42,22 +42,29 @@ class PerceptionPipeline:
         counts, voxel = L1.accumulate_windows(records, edges_ns, self.H, self.W, self.B if want_voxel else None,
                                               sorted_by_time=sorted_by_time)
         frames = torch.empty((T, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
+        self._normalise(counts, frames)
+        return frames, counts, voxel
+
+    def _normalise(self, counts, frames):
+        """counts int32 [N,2,H,W] -> frames fp32 [N,1,h,w]: 0.2*(n+ - n-), optional rectification, centre crop,
+        per-frame 97th-percentile scaling and clip (run.py:334-351, 250-253)."""
+        lib = _lib.load()
+        N = counts.shape[0]
         st = _lib.stream_ptr()
         if self.aligner is None:
-            _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), T, self.H, self.W, self.h, self.w, 0.2,
+            _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), N, self.H, self.W, self.h, self.w, 0.2,
                                              _lib.ptr(frames), st), "evfly_decode_crop")
         else:
-            # run.py:334-351: decode at full resolution, rectify, then centre-crop; only the cropped window of the
-            # remap is computed (the maps are indexed by OUTPUT pixel)
+            # decode at full resolution, rectify, then centre-crop; only the cropped window of the remap is computed
+            # (the maps are indexed by OUTPUT pixel)
             from .calibration_tools import remap_bicubic
-            full = torch.empty((T, self.H, self.W), dtype=torch.float32, device=self.dev)
-            _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), T, self.H, self.W, self.H, self.W, 0.2,
+            full = torch.empty((N, self.H, self.W), dtype=torch.float32, device=self.dev)
+            _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), N, self.H, self.W, self.H, self.W, 0.2,
                                              _lib.ptr(full), st), "evfly_decode_crop")
             mx, my = self.aligner.davis_window(self.h, self.w)
-            remap_bicubic(full, mx, my, out=frames.view(T, self.h, self.w))
-        _lib.check(lib.evfly_quantile_scale_clip(_lib.ptr(frames), T, self.h * self.w, 0.97, -1.0, 1.0, 0.0,
+            remap_bicubic(full, mx, my, out=frames.view(N, self.h, self.w))
+        _lib.check(lib.evfly_quantile_scale_clip(_lib.ptr(frames), N, self.h * self.w, 0.97, -1.0, 1.0, 0.0,
                                                  _lib.ptr(frames), None, st), "evfly_quantile_scale_clip")
-        return frames, counts, voxel
 
     # ---- L3 ----------------------------------------------------------------------------------------
     def forward(self, frames, carry_state=True):
@@ -69,18 +76,32 @@ class PerceptionPipeline:
             self.state_unet, self.state_vit = hu, hv
         return vel, depth
 
+    def frames_from_trajectories(self, records_list, edges_list, want_voxel=True):
+        """L1 + L2 for n trajectories of equal length T: each trajectory is accumulated from its own event stream into
+        its slice of one [n,T,...] buffer, then ONE decode(+rectify)+crop and ONE quantile launch cover all n*T frames
+        (the per-frame work is independent). Returns (frames [T*n,1,h,w] in time-major order t*n + s, counts
+        [n,T,2,H,W], voxel [n,T,B,H,W] | None)."""
+        lib = _lib.load()
+        n = len(records_list)
+        T = edges_list[0].shape[0] - 1
+        assert all(e.shape[0] - 1 == T for e in edges_list), "trajectories must have the same number of windows"
+        counts = torch.empty((n, T, 2, self.H, self.W), dtype=torch.int32, device=self.dev)
+        voxel = torch.empty((n, T, self.B, self.H, self.W), dtype=torch.float32, device=self.dev) if want_voxel else None
+        for s, (rec, edges) in enumerate(zip(records_list, edges_list)):
+            L1.accumulate_windows(rec, edges, self.H, self.W, self.B if want_voxel else None, counts=counts[s],
+                                  voxel=None if voxel is None else voxel[s])
+        frames = torch.empty((n, T, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
+        self._normalise(counts.view(n * T, 2, self.H, self.W), frames.view(n * T, 1, self.h, self.w))
+        return frames.transpose(0, 1).reshape(T * n, 1, self.h, self.w), counts, voxel
+
     def run_trajectories(self, records_list, edges_list, want_voxel=True):
         """Config 4: several independent trajectories of equal length T on one GPU. Each trajectory is accumulated
         on its own (its events are its own stream); the model then advances all of them together, frames in
         time-major order, so the recurrent scans run n_traj-wide. Fresh state. Returns (vel [n_traj,T,3], depth
         [n_traj,T,1,h,w])."""
         n = len(records_list)
-        frames = []
-        for rec, edges in zip(records_list, edges_list):
-            f, _, _ = self.frames_from_windows(rec, edges, want_voxel)
-            frames.append(f)
-        T = frames[0].shape[0]
-        tm = torch.stack(frames, dim=1).reshape(T * n, 1, self.h, self.w)        # frame t*n + s
+        tm = self.frames_from_trajectories(records_list, edges_list, want_voxel)[0]
+        T = tm.shape[0] // n
         desvel = torch.full((T * n, 1), self.desvel, dtype=torch.float32, device=self.dev)
         vel, (depth, _, _) = self.model.forward_trajectories([tm, desvel, [None, None], None], n)
         return vel.view(T, n, 3).transpose(0, 1), depth.view(T, n, 1, self.h, self.w).transpose(0, 1)
