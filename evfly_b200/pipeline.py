@@ -158,6 +158,8 @@ class TrajectoryFeeder:
             return
         self._stage(0, self._as_lists(cur)[0])
         slot = 0
+        pending = None          # (slot, view) of the previous batch: its result is handed out one batch late, so the
+                                # host is always one batch ahead of the GPU and the launch queue never drains
         while cur is not None:
             nxt = next(it, None)
             if nxt is not None:
@@ -179,9 +181,14 @@ class TrajectoryFeeder:
                 out.copy_(vel, non_blocking=True)
             self.free[slot].record(main)
             self.done[slot].record(main)
-            self.done[slot].synchronize()
-            yield out
+            if pending is not None:
+                self.done[pending[0]].synchronize()
+                yield pending[1]
+            pending = (slot, out)
             cur, slot = nxt, slot ^ 1
+        if pending is not None:
+            self.done[pending[0]].synchronize()
+            yield pending[1]
 
 
 class StreamingSession:
