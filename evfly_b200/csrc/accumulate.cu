@@ -182,20 +182,35 @@ k_voxel_finalize(float4* __restrict__ stage, unsigned HW, int B, int* __restrict
 // T windows of one stream
 // ---------------------------------------------------------------------------------------
 // r[w] = first event index with t >= edges[w] (stream sorted by time)
-__global__ void k_window_ranges(const uint4* __restrict__ ev, int64_t n,
-                                const int64_t* __restrict__ edges, int T,
-                                int64_t* __restrict__ ranges) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per edge, 33-ary search: every round the 32 lanes probe 32 evenly spaced records of the current interval
+// (5 dependent rounds for 10 M events instead of 24 for a scalar binary search).
+__global__ void __launch_bounds__(128)
+k_window_ranges(const uint4* __restrict__ ev, int64_t n, const int64_t* __restrict__ edges, int T, int64_t* __restrict__ ranges) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w > T) return;
     const int64_t key = edges[w];
-    int64_t lo = 0, hi = n;
+    int64_t lo = 0, hi = n;          // invariant: t[i] < key for i < lo, t[i] >= key for i >= hi
     while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        const uint4 r = ev[mid];
-        const int64_t t = (int64_t)r.y * 1000000000ll + (int64_t)r.z;
-        if (t < key) lo = mid + 1; else hi = mid;
+        const int64_t len = hi - lo;
+        const int64_t step = (len + 32) / 33;                       // >= 1
+        const int64_t pos = lo + (int64_t)(lane + 1) * step - 1;     // probes lo+step-1, lo+2*step-1, ...
+        bool ge = true;                                              // positions past the interval count as >= key
+        if (pos < hi) {
+            const uint4 r = ev[pos];
+            ge = ((int64_t)r.y * 1000000000ll + (int64_t)r.z) >= key;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (m == 0) {                                                // all 32 probes lie inside and are < key
+            lo += 32 * step;
+            continue;
+        }
+        const int first = __ffs(m) - 1;                              // first probe with t >= key (or the first one past hi)
+        const int64_t new_hi = lo + (int64_t)(first + 1) * step - 1; // that probe's position (or beyond hi)
+        const int64_t new_lo = lo + (int64_t)first * step;           // one past the previous probe
+        hi = new_hi < hi ? new_hi : hi;
+        lo = new_lo;
     }
-    ranges[w] = lo;
+    if (lane == 0) ranges[w] = lo;
 }
 
 // events [ranges[w0], ranges[w1]) (or the whole stream when ranges == nullptr) scattered into
@@ -485,7 +500,7 @@ extern "C" int evfly_accumulate_windows(const evfly_event* d_events, int64_t n,
     EVFLY_REQUIRE(sorted_by_time || T + 1 <= max_edges, "accumulate_windows: unsorted streams support T <= %d", max_edges - 1);
 
     if (sorted_by_time && n > 0) {
-        k_window_ranges<<<(T + 1 + 127) / 128, 128, 0, st>>>(ev, n, d_edges_ns, T, d_range_ws);
+        k_window_ranges<<<(T + 1 + 3) / 4, 128, 0, st>>>(ev, n, d_edges_ns, T, d_range_ws);
         EVFLY_LAUNCHED();
     }
     for (int w0 = 0; w0 < T; w0 += G) {
