@@ -40,7 +40,9 @@ struct HaloCfg {
     static constexpr int STAGES = (COUT > 64) ? 3 : 4;          // 64->128: 144 KB of resident weights leave room for 3 halos
     static constexpr int NACC = 4;
     static constexpr int TMEM_COLS = (NACC * COUT <= 128) ? 128 : (NACC * COUT <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = W_BYTES + STAGES * HALO_BYTES + 1024 + 1024;
+    // epilogue staging (8 warps x 32 pixels x COUT bf16) so that global stores are 512-byte contiguous; not for COUT = 128
+    static constexpr int OUT_STAGE_BYTES = (COUT <= 64) ? 8 * 32 * COUT * 2 : 0;
+    static constexpr int SMEM_BYTES = W_BYTES + STAGES * HALO_BYTES + 1024 /*alignment slack*/ + 2048 /*barriers, bias*/ + OUT_STAGE_BYTES;
     static_assert(SMEM_BYTES <= 227 * 1024, "halo conv: weights + halo stages exceed shared memory");
     static constexpr uint32_t LAYOUT = (CIN == 64) ? kLayoutSw128 : kLayoutSw64;
     static constexpr uint32_t SBO_A = 10 * ROW_B;               // next 8-pixel group = next output row = 10 halo rows
@@ -79,6 +81,7 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t* w_bar = tempty_bar + Cfg::NACC;             // [1]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* s_bias = reinterpret_cast<float*>(w_bar + 2);  // [COUT]
+    uint8_t* s_ostage = s_halo + Cfg::STAGES * Cfg::HALO_BYTES + 2048;   // [8 warps][32 px][COUT] bf16 (16-byte chunks XOR-swizzled)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -122,33 +125,39 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             tma_load_4d(s_halo + stage * Cfg::HALO_BYTES, &map_x, &full_bar[stage], 0, tx * 8 - p.pad, ty * 16 - p.pad, n);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ================= MMA issuer =================
+        // The whole warp walks the tile loop convergently and ONE elected lane issues. The descriptors of a tile differ
+        // from the stage's base descriptor only in the start-address field (bits [0,14), units of 16 B), by constants
+        // known at compile time, so an MMA costs one 64-bit add per operand. (Issuing from `lane == 0` with the
+        // descriptors rebuilt per MMA took ~75 clk per instruction; the tensor pipe needs ~40 at N <= 32,
+        // profiles/r1_microbench_mma_rate.json.)
         constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
         mbar_wait(w_bar, 0);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        const uint32_t w_base = smem_u32(s_w);
+        const uint64_t dw0 = make_smem_desc(smem_u32(s_w), Cfg::SBO_B, Cfg::LAYOUT);
+        const uint64_t dh0 = make_smem_desc(smem_u32(s_halo), Cfg::SBO_A, Cfg::LAYOUT);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * COUT);
-            const uint32_t halo = smem_u32(s_halo + stage * Cfg::HALO_BYTES);
+            const uint64_t da0 = dh0 + (uint64_t)(stage * (Cfg::HALO_BYTES >> 4));
+            if (elect_one()) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const int kh = tap / 3, kw = tap % 3;
-                const uint32_t a0 = halo + (uint32_t)((kh * 10 + kw) * Cfg::ROW_B);
-                const uint32_t b0 = w_base + (uint32_t)(tap * Cfg::W_TAP_BYTES);
+                for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                for (int k = 0; k < CIN / 16; ++k) {
-                    const uint64_t da = make_smem_desc(a0 + k * 32, Cfg::SBO_A, Cfg::LAYOUT);
-                    const uint64_t db = make_smem_desc(b0 + k * 32, Cfg::SBO_B, Cfg::LAYOUT);
-                    umma_bf16(tmem_d, da, db, idesc, (tap | k) != 0);
+                    for (int k = 0; k < CIN / 16; ++k) {
+                        const uint64_t da = da0 + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * Cfg::ROW_B + k * 32) >> 4);
+                        const uint64_t db = dw0 + (uint64_t)((tap * Cfg::W_TAP_BYTES + k * 32) >> 4);
+                        umma_bf16(tmem_d, da, db, idesc, (tap | k) != 0);
+                    }
                 }
+                umma_commit(&empty_bar[stage]);
+                umma_commit(&tfull_bar[acc]);
             }
-            umma_commit(&empty_bar[stage]);
-            umma_commit(&tfull_bar[acc]);
+            __syncwarp();
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
@@ -158,6 +167,9 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int grp = (warp - 4) >> 2;
         const int row = ew * 32 + lane;          // tile pixel: r = row / 8, c = row % 8
         const int r = row >> 3, c = row & 7;
+        constexpr bool kStage = Cfg::OUT_STAGE_BYTES > 0;
+        constexpr int kCP = COUT / 8;            // 16-byte chunks per pixel
+        uint8_t* my_stage = s_ostage + (warp - 4) * (32 * COUT * 2);
         constexpr bool kBiasRegs = COUT <= 64;   // bias in registers (same for every tile); from shared memory for wide outputs
         float breg[kBiasRegs ? COUT : 1];
         if constexpr (kBiasRegs) {
@@ -194,7 +206,12 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
                         f[e] = p.relu ? fmaxf(x, 0.f) : x;
                     }
-                    if (ok) reinterpret_cast<uint4*>(o + c0)[q] = pack8_bf16(f);
+                    if constexpr (kStage) {
+                        // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
+                        *reinterpret_cast<uint4*>(my_stage + lane * (COUT * 2) + ((((c0 >> 3) + q) ^ (kCP == 4 ? ((lane >> 1) & 3) : (lane & 7))) << 4)) = pack8_bf16(f);
+                    } else {
+                        if (ok) reinterpret_cast<uint4*>(o + c0)[q] = pack8_bf16(f);
+                    }
                     if (p.pool_out) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -204,6 +221,21 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         if (pool_lane) reinterpret_cast<uint4*>(po + c0)[q] = pack8_bf16(f);
                     }
                 }
+            }
+            if constexpr (kStage) {
+                // write-out: instruction j stores chunks [32j, 32j+32) of the warp's 32 pixels = 512 contiguous bytes
+                // (8 pixels of one output row are adjacent in the NHWC grid)
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < kCP; ++j) {
+                    const int id = j * 32 + lane, px = id / kCP, ch = id % kCP;
+                    const int poh = ty * 16 + ew * 4 + (px >> 3), pow_ = tx * 8 + (px & 7);
+                    if (poh < p.out_vh && pow_ < p.out_vw) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(my_stage + px * (COUT * 2) + ((ch ^ (kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4));
+                        *reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + poh) * p.Wp + pow_) * COUT + ch * 8) = val;
+                    }
+                }
+                __syncwarp();      // the staging rows are rewritten by the next tile of this warp
             }
             tc_fence_before();
             __syncwarp();
