@@ -16,7 +16,7 @@
 //
 // Kernel anatomy (one CTA = 256 threads, persistent over output tiles):
 //   warp 0 lane 0 : TMA producer  (A box + B box per K-block -> smem ring, mbarrier expect_tx)
-//   warp 1 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::f16, M=128, N=TN, K=16)
+//   warp 1        : MMA issuer    (tcgen05.mma.cta_group::1.kind::f16, M=128, N=TN, K=16; one elected lane)
 //   warp 2        : TMEM allocator (2 accumulator buffers of TN fp32 columns)
 //   warps 4..7    : epilogue      (tcgen05.ld 32x32b -> +bias -> ReLU -> bf16 -> 16-byte stores)
 #include "tc_common.cuh"
@@ -153,13 +153,18 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ================= MMA issuer =================
+        // whole warp convergent, one elected lane issues; per MMA the descriptors are the stage's base descriptors plus
+        // a compile-time constant in the start-address field (see tc_conv_halo.cu and profiles/r1_microbench_mma_rate.json:
+        // rebuilding them from `lane == 0` costs ~75 clk per instruction, more than an N <= 128 MMA takes)
         constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, TN);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const uint64_t da_base = make_smem_desc(smem_u32(smem), Cfg::SBO, Cfg::LAYOUT);
+        const uint64_t db_base = make_smem_desc(smem_u32(smem) + Cfg::A_BYTES, Cfg::SBO, Cfg::LAYOUT);
         for (int step = 0; step < p.n_steps; ++step)
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -168,18 +173,18 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int kb = 0; kb < k_blocks; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                const uint32_t sb = sa + Cfg::A_BYTES;
+                const uint64_t soff = (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                    const uint64_t da = make_smem_desc(sa + k * 32, Cfg::SBO, Cfg::LAYOUT);
-                    const uint64_t db = make_smem_desc(sb + k * 32, Cfg::SBO, Cfg::LAYOUT);
-                    umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+                    for (int k = 0; k < KC / 16; ++k)
+                        umma_bf16(tmem_d, da_base + soff + (uint64_t)(k * 2), db_base + soff + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+            if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+            __syncwarp();
             if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
