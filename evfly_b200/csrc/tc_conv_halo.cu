@@ -65,6 +65,91 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// Epilogue shared by the two halo kernels: warps 4-7 take the even local tiles, warps 8-11 the odd ones.
+template <int COUT, int NACC, bool STAGE_OUT>
+__device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int lane, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                              const float* s_bias, uint8_t* s_ostage, int total_tiles, int tiles_per_img) {
+    // ================= epilogue: group 0 = warps 4-7 (even local tiles), group 1 = warps 8-11 (odd) =====
+    const int ew = (warp - 4) & 3;           // TMEM lanes [32*ew, 32*ew+32) (a warp may only touch lanes of warp%4)
+    const int grp = (warp - 4) >> 2;
+    const int row = ew * 32 + lane;          // tile pixel: r = row / 8, c = row % 8
+    const int r = row >> 3, c = row & 7;
+    constexpr bool kStage = STAGE_OUT;
+    constexpr int kCP = COUT / 8;            // 16-byte chunks per pixel
+    uint8_t* my_stage = s_ostage + (warp - 4) * (32 * COUT * 2);
+    constexpr bool kBiasRegs = COUT <= 64;   // bias in registers (same for every tile); from shared memory for wide outputs
+    float breg[kBiasRegs ? COUT : 1];
+    if constexpr (kBiasRegs) {
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) breg[j] = s_bias[j];
+    }
+    int it = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+        const int acc = it & (NACC - 1);
+        const uint32_t acc_phase = (uint32_t)(it / NACC) & 1u;
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int oh = ty * 16 + r, ow = tx * 8 + c;
+        const bool ok = oh < p.out_vh && ow < p.out_vw;
+        __nv_bfloat16* o = p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT;
+        // fused 2x2 max-pool: the partners of pixel (r, c) are lanes ^1 (column) and ^8 (row) of the same warp;
+        // the lane with even r and even c writes. max commutes with the (monotonic) bf16 rounding, so the
+        // result is bit-identical to pooling the stored tensor.
+        const bool pool_lane = p.pool_out != nullptr && ((lane & 9) == 0) && oh + 1 < p.out_vh && ow + 1 < p.out_vw;
+        __nv_bfloat16* po = p.pool_out ? p.pool_out + (((long long)n * p.Hp2 + (oh >> 1)) * p.Wp2 + (ow >> 1)) * COUT : nullptr;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * COUT + c0), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
+                    f[e] = p.relu ? fmaxf(x, 0.f) : x;
+                }
+                if constexpr (kStage) {
+                    // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
+                    *reinterpret_cast<uint4*>(my_stage + lane * (COUT * 2) + ((((c0 >> 3) + q) ^ (kCP == 4 ? ((lane >> 1) & 3) : (lane & 7))) << 4)) = pack8_bf16(f);
+                } else {
+                    if (ok) reinterpret_cast<uint4*>(o + c0)[q] = pack8_bf16(f);
+                }
+                if (p.pool_out) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
+                        f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 8));
+                    }
+                    if (pool_lane) reinterpret_cast<uint4*>(po + c0)[q] = pack8_bf16(f);
+                }
+            }
+        }
+        if constexpr (kStage) {
+            // write-out: instruction j stores chunks [32j, 32j+32) of the warp's 32 pixels = 512 contiguous bytes
+            // (8 pixels of one output row are adjacent in the NHWC grid)
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < kCP; ++j) {
+                const int id = j * 32 + lane, px = id / kCP, ch = id % kCP;
+                const int poh = ty * 16 + ew * 4 + (px >> 3), pow_ = tx * 8 + (px & 7);
+                if (poh < p.out_vh && pow_ < p.out_vw) {
+                    const uint4 val = *reinterpret_cast<const uint4*>(my_stage + px * (COUT * 2) + ((ch ^ (kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4));
+                    *reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + poh) * p.Wp + pow_) * COUT + ch * 8) = val;
+                }
+            }
+            __syncwarp();      // the staging rows are rewritten by the next tile of this warp
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+}
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(384, 1)
 k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloArgs p) {
@@ -162,85 +247,154 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ================= epilogue: group 0 = warps 4-7 (even local tiles), group 1 = warps 8-11 (odd) =====
-        const int ew = (warp - 4) & 3;           // TMEM lanes [32*ew, 32*ew+32) (a warp may only touch lanes of warp%4)
-        const int grp = (warp - 4) >> 2;
-        const int row = ew * 32 + lane;          // tile pixel: r = row / 8, c = row % 8
-        const int r = row >> 3, c = row & 7;
-        constexpr bool kStage = Cfg::OUT_STAGE_BYTES > 0;
-        constexpr int kCP = COUT / 8;            // 16-byte chunks per pixel
-        uint8_t* my_stage = s_ostage + (warp - 4) * (32 * COUT * 2);
-        constexpr bool kBiasRegs = COUT <= 64;   // bias in registers (same for every tile); from shared memory for wide outputs
-        float breg[kBiasRegs ? COUT : 1];
-        if constexpr (kBiasRegs) {
-#pragma unroll
-            for (int j = 0; j < COUT; ++j) breg[j] = s_bias[j];
+        halo_epilogue<COUT, Cfg::NACC, (Cfg::OUT_STAGE_BYTES > 0)>(p, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_ostage, total_tiles, tiles_per_img);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Cin = 128 layers (e32, d32, d41, e41): the weights (9 x COUT x 128 bf16, up to 590 KB) cannot stay in shared memory,
+// but the input halo still can. Per 16x8 output tile the halo is loaded ONCE as two 64-channel chunks (two 4-D TMA
+// boxes of 180 rows x 128 B, double-buffered across tiles) and the 18 weight blocks [COUT x 64] of (chunk, tap) stream
+// through a small ring. Against the tap-streaming kernel (A tile + B block per K-block) the L2 -> SM traffic per tile
+// drops from 18 x (16 + B) KB to 46 + 18 x B KB, which is what bounds these layers (they sat at 560-880 TFLOP/s with
+// the tensor pipe a third busy).
+// ---------------------------------------------------------------------------------------
+template <int COUT>
+struct HaloWsCfg {
+    static constexpr int CHUNK_BYTES = ((180 * 128 + 1023) / 1024) * 1024;      // one 64-channel halo chunk, 128-byte rows
+    static constexpr int A_BYTES = 2 /*tile buffers*/ * 2 /*chunks*/ * CHUNK_BYTES;
+    static constexpr int B_BLOCK = COUT * 128;                                   // [COUT rows][64 ch] bf16
+    static constexpr int NB = (COUT <= 128) ? 6 : 3;                             // weight ring slots
+    static constexpr int NACC = (COUT <= 128) ? 4 : 2;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int OUT_STAGE_BYTES = (COUT <= 64) ? 8 * 32 * COUT * 2 : 0;
+    static constexpr int SMEM_BYTES = A_BYTES + NB * B_BLOCK + 1024 + 2048 + OUT_STAGE_BYTES;
+    static_assert(SMEM_BYTES <= 227 * 1024, "weight-streaming halo conv: shared memory");
+    static constexpr uint32_t SBO_A = 10 * 128, SBO_B = 8 * 128;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(384, 1)
+k_tc_conv3x3_halo_ws(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloArgs p) {
+    using Cfg = HaloWsCfg<COUT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_a = smem;                                  // [2 buffers][2 chunks][180 rows][128 B]
+    uint8_t* s_b = smem + Cfg::A_BYTES;                   // [NB][COUT][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + Cfg::NB * Cfg::B_BLOCK);
+    uint64_t* a_full = bars;                              // [2]
+    uint64_t* a_empty = bars + 2;                         // [2]
+    uint64_t* b_full = bars + 4;                          // [NB]
+    uint64_t* b_empty = b_full + Cfg::NB;                 // [NB]
+    uint64_t* tfull_bar = b_empty + Cfg::NB;              // [NACC]
+    uint64_t* tempty_bar = tfull_bar + Cfg::NACC;         // [NACC]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + Cfg::NACC);
+    float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);       // [COUT]
+    uint8_t* s_ostage = s_b + Cfg::NB * Cfg::B_BLOCK + 2048;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int total_tiles = tiles_per_img * p.N;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
         }
-        int it = grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
-            const int acc = it & (Cfg::NACC - 1);
-            const uint32_t acc_phase = (uint32_t)(it / Cfg::NACC) & 1u;
+        for (int i = 0; i < Cfg::NB; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int a = 0; a < Cfg::NACC; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int slot = 0;
+        uint32_t b_phase = 0;
+        int it = 0;
+        auto load_halo = [&](int tile, int j) {       // j = running local tile index -> buffer j & 1
+            const int buf = j & 1;
             const int n = tile / tiles_per_img;
             const int rem = tile - n * tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-            const int oh = ty * 16 + r, ow = tx * 8 + c;
-            const bool ok = oh < p.out_vh && ow < p.out_vw;
-            __nv_bfloat16* o = p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT;
-            // fused 2x2 max-pool: the partners of pixel (r, c) are lanes ^1 (column) and ^8 (row) of the same warp;
-            // the lane with even r and even c writes. max commutes with the (monotonic) bf16 rounding, so the
-            // result is bit-identical to pooling the stored tensor.
-            const bool pool_lane = p.pool_out != nullptr && ((lane & 9) == 0) && oh + 1 < p.out_vh && ow + 1 < p.out_vw;
-            __nv_bfloat16* po = p.pool_out ? p.pool_out + (((long long)n * p.Hp2 + (oh >> 1)) * p.Wp2 + (ow >> 1)) * COUT : nullptr;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * COUT + c0), v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
-                        f[e] = p.relu ? fmaxf(x, 0.f) : x;
-                    }
-                    if constexpr (kStage) {
-                        // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
-                        *reinterpret_cast<uint4*>(my_stage + lane * (COUT * 2) + ((((c0 >> 3) + q) ^ (kCP == 4 ? ((lane >> 1) & 3) : (lane & 7))) << 4)) = pack8_bf16(f);
-                    } else {
-                        if (ok) reinterpret_cast<uint4*>(o + c0)[q] = pack8_bf16(f);
-                    }
-                    if (p.pool_out) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
-                            f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 8));
-                        }
-                        if (pool_lane) reinterpret_cast<uint4*>(po + c0)[q] = pack8_bf16(f);
-                    }
-                }
+            mbar_wait(&a_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
+            mbar_expect_tx(&a_full[buf], 2 * 180 * 128);
+            tma_load_4d(s_a + (buf * 2 + 0) * Cfg::CHUNK_BYTES, &map_x, &a_full[buf], 0, tx * 8 - p.pad, ty * 16 - p.pad, n);
+            tma_load_4d(s_a + (buf * 2 + 1) * Cfg::CHUNK_BYTES, &map_x, &a_full[buf], 64, tx * 8 - p.pad, ty * 16 - p.pad, n);
+        };
+        if ((int)blockIdx.x < total_tiles) load_halo(blockIdx.x, 0);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int blk = 0; blk < 18; ++blk) {                                                // (chunk, tap) = (blk / 9, blk % 9)
+                // prefetch the next tile's halo once this tile's first weight blocks are on their way (its buffer is
+                // released by the previous tile's last MMA, which has retired by then)
+                if (blk == 9 && tile + (int)gridDim.x < total_tiles) load_halo(tile + gridDim.x, it + 1);
+                mbar_wait(&b_empty[slot], b_phase ^ 1);
+                mbar_expect_tx(&b_full[slot], Cfg::B_BLOCK);
+                tma_load_2d(s_b + slot * Cfg::B_BLOCK, &map_w, &b_full[slot], (blk % 9) * 128 + (blk / 9) * 64, 0);
+                if (++slot == Cfg::NB) { slot = 0; b_phase ^= 1; }
             }
-            if constexpr (kStage) {
-                // write-out: instruction j stores chunks [32j, 32j+32) of the warp's 32 pixels = 512 contiguous bytes
-                // (8 pixels of one output row are adjacent in the NHWC grid)
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < kCP; ++j) {
-                    const int id = j * 32 + lane, px = id / kCP, ch = id % kCP;
-                    const int poh = ty * 16 + ew * 4 + (px >> 3), pow_ = tx * 8 + (px & 7);
-                    if (poh < p.out_vh && pow_ < p.out_vw) {
-                        const uint4 val = *reinterpret_cast<const uint4*>(my_stage + px * (COUT * 2) + ((ch ^ (kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4));
-                        *reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + poh) * p.Wp + pow_) * COUT + ch * 8) = val;
-                    }
-                }
-                __syncwarp();      // the staging rows are rewritten by the next tile of this warp
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
+    } else if (warp == 1) {
+        // ================= MMA issuer (convergent warp, one elected lane) =================
+        constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+        const uint64_t da_base = make_smem_desc(smem_u32(s_a), Cfg::SBO_A, kLayoutSw128);
+        const uint64_t db_base = make_smem_desc(smem_u32(s_b), Cfg::SBO_B, kLayoutSw128);
+        int slot = 0, acc = 0, it = 0;
+        uint32_t b_phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            mbar_wait(&a_full[buf], ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * COUT);
+#pragma unroll 1
+            for (int chunk = 0; chunk < 2; ++chunk) {
+                const uint64_t da_c = da_base + (uint64_t)(((buf * 2 + chunk) * Cfg::CHUNK_BYTES) >> 4);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&b_full[slot], b_phase);
+                    tc_fence_after();
+                    const uint64_t db_s = db_base + (uint64_t)((slot * Cfg::B_BLOCK) >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_d, da_c + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * 128 + k * 32) >> 4), db_s + (uint64_t)(k * 2), idesc,
+                                      (chunk | tap | k) != 0);
+                        umma_commit(&b_empty[slot]);
+                    }
+                    __syncwarp();
+                    if (++slot == Cfg::NB) { slot = 0; b_phase ^= 1; }
+                }
+            }
+            if (elect_one()) {
+                umma_commit(&a_empty[buf]);
+                umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        halo_epilogue<COUT, Cfg::NACC, (Cfg::OUT_STAGE_BYTES > 0)>(p, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_ostage, total_tiles, tiles_per_img);
     }
     tc_fence_before();
     __syncthreads();
@@ -251,7 +405,7 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // input grid [N, Hp, Wp, C] as a 4-D tensor (C fastest), box [1, 18, 10, C]
-static int make_map_halo(CUtensorMap* map, const void* base, int N, int Hp, int Wp, int C) {
+static int make_map_halo(CUtensorMap* map, const void* base, int N, int Hp, int Wp, int C, int box_c = 0) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -259,9 +413,10 @@ static int make_map_halo(CUtensorMap* map, const void* base, int N, int Hp, int 
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)C, 10, 18, 1};
+    if (box_c == 0) box_c = C;
+    cuuint32_t box[4] = {(cuuint32_t)box_c, 10, 18, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    const CUtensorMapSwizzle sw = (C * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle sw = (box_c * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -271,14 +426,15 @@ static int make_map_halo(CUtensorMap* map, const void* base, int N, int Hp, int 
     return EVFLY_OK;
 }
 
-static int make_map_w(CUtensorMap* map, const void* base, int Cout, int Cin) {
+static int make_map_w(CUtensorMap* map, const void* base, int Cout, int Cin, int box_k = 0) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return EVFLY_ERR_CUDA;
     cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)9 * Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)Cin, (cuuint32_t)Cout};
+    if (box_k == 0) box_k = Cin;
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)Cout};
     cuuint32_t es[2] = {1, 1};
-    const CUtensorMapSwizzle sw = (Cin * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle sw = (box_k * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -308,6 +464,26 @@ static int launch_halo(const void* x, const void* w, const HaloArgs& p, cudaStre
     return EVFLY_OK;
 }
 
+template <int COUT>
+static int launch_halo_ws(const void* x, const void* w, const HaloArgs& p, cudaStream_t st) {
+    using Cfg = HaloWsCfg<COUT>;
+    CUtensorMap mx, mw;
+    int rc = make_map_halo(&mx, x, p.N, p.Hp, p.Wp, 128, 64);
+    if (rc) return rc;
+    rc = make_map_w(&mw, w, COUT, 128, 64);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv3x3_halo_ws<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * p.N;
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    k_tc_conv3x3_halo_ws<COUT><<<grid, 384, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
 }  // namespace evfly
 
 using namespace evfly;
@@ -315,8 +491,8 @@ using namespace evfly;
 static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp, int Wp,
                      int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream, int pad = 0) {
     EVFLY_REQUIRE(d_x && d_w && d_out && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
-    EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128),
-                  "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64} or (64,128) (got %d, %d)", Cin, Cout);
+    EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128) || (Cin == 128 && (Cout == 64 || Cout == 128 || Cout == 256)),
+                  "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64}, (64,128) or (128, 64|128|256) (got %d, %d)", Cin, Cout);
     HaloArgs p;
     p.bias = d_bias;
     p.out = reinterpret_cast<__nv_bfloat16*>(d_out);
@@ -335,6 +511,9 @@ static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void
     EVFLY_REQUIRE(!d_pool || (Hp2 >= (vh - 2) / 2 && Wp2 >= (vw - 2) / 2), "tc_conv3x3_halo_pool_bf16: pooled grid smaller than (vh-2)/2 x (vw-2)/2");
     EVFLY_REQUIRE((long long)p.tiles_x * p.tiles_y * N < (1ll << 31), "tc_conv3x3_halo_bf16: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 128 && Cout == 64) return launch_halo_ws<64>(d_x, d_w, p, st);
+    if (Cin == 128 && Cout == 128) return launch_halo_ws<128>(d_x, d_w, p, st);
+    if (Cin == 128 && Cout == 256) return launch_halo_ws<256>(d_x, d_w, p, st);
     if (Cin == 64 && Cout == 128) return launch_halo<64, 128>(d_x, d_w, p, st);
     if (Cin == 32 && Cout == 32) return launch_halo<32, 32>(d_x, d_w, p, st);
     if (Cin == 32 && Cout == 64) return launch_halo<32, 64>(d_x, d_w, p, st);

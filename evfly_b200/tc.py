@@ -70,7 +70,7 @@ def _call_halo_pool(*args):
 
 
 def _halo_ok(cin, cout):
-    return USE_HALO and ((cin in (32, 64) and cout in (32, 64)) or (cin == 64 and cout == 128))
+    return USE_HALO and ((cin in (32, 64) and cout in (32, 64)) or (cin == 64 and cout == 128) or (cin == 128 and cout in (64, 128, 256)))
 
 
 def conv3x3_pool(g: Grid, w_packed, bias, relu=True):

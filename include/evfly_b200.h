@@ -463,7 +463,8 @@ int evfly_dwconv3x3_gelu_nhwc_bf16(const void* d_x, const float* d_w, const floa
 int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float* d_h0, const float* d_c0,
                          float* d_hs, float* d_hT, float* d_cT, int T, int H, int n_seq, void* stream);
 
-/* 3x3 valid conv + bias (+ReLU) for Cin, Cout in {32, 64} (and 64 -> 128) with the input halo reused from shared memory
+/* 3x3 valid conv + bias (+ReLU) for Cin, Cout in {32, 64} (and 64 -> 128; Cin = 128 -> 64|128|256 with the weights
+ * streamed through a ring instead of resident) with the input halo reused from shared memory
  * (one 4-D TMA box [18 x 10 pixels] per 16x8 output tile, all 9 taps read through shifted UMMA
  * descriptors, weights resident): x bf16 [N,Hp,Wp,Cin] valid vh x vw, w bf16 [Cout, 9*Cin] ([Cout][tap][Cin]),
  * out bf16 [N,Hp,Wp,Cout]; only the valid (vh-2) x (vw-2) outputs are written.                         */

@@ -214,7 +214,9 @@ def test_shifted_descriptor_probe(cuda_lib):
 
 @pytest.mark.parametrize("N,H,W,vh,vw,Cin,Cout", [(2, 20, 24, 20, 24, 32, 32), (1, 37, 29, 35, 27, 64, 64), (3, 19, 11, 19, 11, 32, 64),
                                                   (1, 72, 152, 72, 152, 64, 32), (2, 18, 10, 18, 10, 32, 32), (1, 5, 5, 3, 3, 64, 64),
-                                                  (2, 41, 53, 40, 50, 64, 128), (1, 126, 170, 126, 169, 64, 128)])
+                                                  (2, 41, 53, 40, 50, 64, 128), (1, 126, 170, 126, 169, 64, 128),
+                                                  # Cin = 128: halo reuse with the weights streamed through a ring
+                                                  (2, 41, 53, 40, 50, 128, 128), (1, 62, 83, 62, 83, 128, 64), (3, 31, 41, 29, 39, 128, 256), (5, 20, 19, 20, 19, 128, 128)])
 def test_halo_conv_equals_reference_and_streaming_kernel(cuda_lib, N, H, W, vh, vw, Cin, Cout):
     x = bf(rnd(N, Cin, vh, vw, seed=1))
     w = bf(rnd(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5))
@@ -242,7 +244,7 @@ def test_stem_tensor_core_matches_reference(cuda_lib, N, cin, H, W):
     check_bf16(tc.grid_to_nchw(out.data, H - 2, W - 2), F.relu(F.conv2d(bf(xs).double(), bf(ws).double(), bs.double())), "stem tc")
 
 
-@pytest.mark.parametrize("N,vh,vw,Cin,Cout", [(2, 20, 24, 32, 32), (1, 37, 29, 64, 64), (3, 19, 13, 32, 64), (1, 71, 150, 64, 128), (1, 4, 4, 32, 32)])
+@pytest.mark.parametrize("N,vh,vw,Cin,Cout", [(2, 20, 24, 32, 32), (1, 37, 29, 64, 64), (3, 19, 13, 32, 64), (1, 71, 150, 64, 128), (1, 4, 4, 32, 32), (2, 60, 81, 128, 128)])
 def test_halo_conv_fused_maxpool_is_bit_identical_to_separate_pool(cuda_lib, N, vh, vw, Cin, Cout):
     """learner_models.py OrigUNet: pool(relu(conv(x))). The fused epilogue pools fp32 values before rounding to bf16;
     rounding is monotonic, so the result must equal the stand-alone pool of the stored bf16 tensor bit for bit."""
