@@ -8,14 +8,8 @@
 #include "../../evfly_b200/csrc/tc_common.cuh"
 using namespace evfly;
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
-
 // variant 1: the WHOLE warp 0 runs the issue loop convergently, one elected lane issues (no divergent region)
-__global__ void __launch_bounds__(128) k_rate_elect(int N, uint32_t layout, uint32_t row_bytes, int iters, long long* out) {
+__global__ void __launch_bounds__(128) k_rate_elect(int N, uint32_t layout, uint32_t row_bytes, int iters, long long* out, int shift_rows = 0, int sbo_rows = 8) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_tmem;
@@ -29,7 +23,7 @@ __global__ void __launch_bounds__(128) k_rate_elect(int N, uint32_t layout, uint
     if (threadIdx.x < 32) {
         const uint32_t a = smem_u32(smem), b = smem_u32(smem + 32768);
         const uint32_t idesc = make_idesc_bf16(128, N);
-        const uint64_t da = make_smem_desc(a, 8 * row_bytes, layout), db = make_smem_desc(b, 8 * row_bytes, layout);
+        const uint64_t da = make_smem_desc(a + shift_rows * row_bytes, sbo_rows * row_bytes, layout), db = make_smem_desc(b, 8 * row_bytes, layout);
         fence_proxy_async();
         if (elect_one()) {
             for (int i = 0; i < 8; ++i) umma_bf16(tm, da, db, idesc, i > 0);
@@ -103,6 +97,14 @@ int main() {
             cudaError_t e2 = cudaMemcpy(&c2, d_out, 8, cudaMemcpyDeviceToHost);
             printf("{\"layout\": \"%s\", \"N\": %d, \"cycles_per_mma_one_thread\": %.1f, \"cycles_per_mma_elect_warp\": %.1f, \"err\": \"%s/%s\"}\n", l.name, N,
                    (double)c / iters, (double)c2 / iters, cudaGetErrorString(e), cudaGetErrorString(e2));
+        }
+    // halo-style A operand: descriptor starts `shift` rows into the tile, 8-row groups 10 rows apart (tc_conv_halo.cu)
+    for (auto& l : L)
+        for (int shift : {0, 1, 2, 3, 10, 11, 21, 22}) {
+            long long c2 = 0;
+            k_rate_elect<<<1, 128, 68 * 1024>>>(32, l.layout, l.row, iters, d_out, shift, 10);
+            cudaError_t e2 = cudaMemcpy(&c2, d_out, 8, cudaMemcpyDeviceToHost);
+            printf("{\"layout\": \"%s\", \"N\": 32, \"halo_shift_rows\": %d, \"sbo_rows\": 10, \"cycles_per_mma_elect_warp\": %.1f, \"err\": \"%s\"}\n", l.name, shift, (double)c2 / iters, cudaGetErrorString(e2));
         }
     return 0;
 }
