@@ -66,7 +66,9 @@ struct TcCfg {
     static constexpr int STAGES = STAGES_FIT > 10 ? 10 : (STAGES_FIT < 3 ? 3 : STAGES_FIT);
     static constexpr int NACC = (TN <= 64) ? 4 : 2;            // TMEM accumulator buffers
     static constexpr int BIAS_FLOATS = 2048;                   // bias of every GEMM column, staged once per CTA
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_FLOATS * 4;
+    static constexpr int OUT_STAGE_BYTES = 8 * 2048;           // per epilogue warp: one 32-row x 64-byte slab, transposed for contiguous stores
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_FLOATS * 4 + OUT_STAGE_BYTES;
+    static_assert(SMEM_BYTES <= 227 * 1024, "k_tc_conv_bf16: shared memory");
     static constexpr int TMEM_COLS = (NACC * TN <= 32) ? 32 : (NACC * TN <= 64 ? 64 : (NACC * TN <= 128 ? 128 : (NACC * TN <= 256 ? 256 : 512)));
     static constexpr uint32_t LAYOUT = (KC == 64) ? kLayoutSw128 : kLayoutSw64;
     static constexpr uint32_t SBO = 8 * KC * 2;  // 8 rows x row bytes
@@ -85,6 +87,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + Cfg::NACC;    // [NACC]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 2 * Cfg::NACC);
     float* s_bias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+    uint8_t* s_ostage = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::BIAS_FLOATS * 4;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m_tiles = (p.M_rows + Cfg::BM - 1) / Cfg::BM;
@@ -227,7 +230,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN + c0), r);
                 tmem_ld_wait();
                 const int n_first = nt * TN + c0;
-                if (row_ok && n_first < p.n_rows) {
+                if (n_first < p.n_rows) {            // warp-uniform; rows past the end / outside the valid region are masked per lane below
                     int ch0 = n_first;
                     if (p.convt) {
                         const int phs = n_first / p.cout_t;  // a 32-column slab never straddles a phase (cout_t % 32 == 0)
@@ -239,7 +242,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const float* sb = s_bias + n_first;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
-                    if (res_step) {
+                    if (res_step && row_ok) {
                         const float* rp = res_step + m * (long long)p.n_rows + n_first;
                         if (n_first + 32 <= p.n_rows && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
@@ -252,7 +255,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 if (n_first + j < p.n_rows) v[j] += rp[j];
                         }
                     }
-                    if (p.res16) {
+                    if (p.res16 && row_ok) {
                         const __nv_bfloat16* rp = p.res16 + m * (long long)p.n_rows + n_first;
                         if (n_first + 32 <= p.n_rows && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
@@ -277,6 +280,7 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     const int ncols = min(32, p.n_rows - n_first);
                     if (p.lstm_c) {
+                      if (row_ok) {
                         // columns [n_first, n_first+32) = 8 channels x {i,f,o,g}: the whole cell update
                         // happens here, the gate pre-activations never go to memory (convlstm.py:44-53)
                         const int Ch = p.n_rows >> 2, ch0l = n_first >> 2;
@@ -298,8 +302,10 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
                         pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
                         *reinterpret_cast<uint4*>(lstm_h_step + m * (long long)Ch + ch0l) = pk;
+                      }
                     } else
                     if (p.out_f32) {
+                      if (row_ok) {
                         float* o = p.out_f32 + dst_pix * p.out_ld + p.out_c0 + ch0;
                         if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
@@ -308,7 +314,36 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         } else {
                             for (int j = 0; j < ncols; ++j) o[j] = v[j];
                         }
-                    } else {
+                      }
+                    } else if (ncols == 32 && (p.out_ld & 7) == 0 && ((p.out_c0 + ch0) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+                        // bf16 slab of 32 rows x 64 bytes: transposed through shared memory so that one store instruction writes
+                        // 8 rows x 64 contiguous bytes (full sectors; 512 contiguous bytes when the rows are adjacent) instead of
+                        // 32 scattered 16-byte pieces. Warp-uniform branch.
+                        uint8_t* st = s_ostage + (warp - 4) * 2048;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 pk;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
+                            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
+                            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                            *reinterpret_cast<uint4*>(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pk;
+                        }
+                        __syncwarp();
+                        const long long row_elem = row_ok ? dst_pix * p.out_ld : -1;      // element offset of this lane's row, -1 = masked
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int rr = j * 8 + (lane >> 2), ch = lane & 3;
+                            const long long re = __shfl_sync(0xffffffffu, row_elem, rr);
+                            const uint4 val = *reinterpret_cast<const uint4*>(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                            if (re >= 0) *reinterpret_cast<uint4*>(p.out + re + p.out_c0 + ch0 + ch * 8) = val;
+                        }
+                        __syncwarp();
+                    } else if (row_ok) {
                         __nv_bfloat16* o = p.out + dst_pix * p.out_ld + p.out_c0 + ch0;
                         if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
