@@ -377,6 +377,26 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 __threadfence();   // cumulative: orders the other epilogue threads' (fenced, barrier-ordered) stores too
                 atomicAdd(p.sync_counter, 1u);
             }
+            // While the other CTAs arrive and the next step's operands stream in, pull the NEXT step's fp32 gate
+            // pre-activations (res = W_x * x + b, precomputed for all steps, far larger than L2) into L2: they do not
+            // depend on h, and the fused cell update would otherwise wait for DRAM on the critical path of every step.
+            // (Pre-issuing the weight loads before the barrier was tried as well and changed nothing.)
+            if (p.res && step + 1 < p.n_steps) {
+                const float* nxt = p.res + (long long)(step + 1) * p.res_step;
+                const int e = threadIdx.x - 128, rr = e & 127, part = e >> 7;       // 2 threads per row
+                for (long long j = 0; j < n_local; ++j) {
+                    const long long tile = blockIdx.x + j * gridDim.x;
+                    const long long mt = tile / n_tiles;
+                    const int nt = (int)(tile - mt * n_tiles);
+                    const long long m = mt * Cfg::BM + rr;
+                    if (m < p.M_rows) {
+                        const char* row = reinterpret_cast<const char*>(nxt + m * (long long)p.n_rows + nt * TN);
+                        const int bytes = min(TN, p.n_rows - nt * TN) * 4;
+                        for (int off = part * 128; off < bytes; off += 256)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+                    }
+                }
+            }
         }
         }
     }
