@@ -76,11 +76,12 @@ class PerceptionPipeline:
             self.state_unet, self.state_vit = hu, hv
         return vel, depth
 
-    def frames_from_trajectories(self, records_list, edges_list, want_voxel=True):
+    def frames_from_trajectories(self, records_list, edges_list, want_voxel=True, ready=None):
         """L1 + L2 for n trajectories of equal length T: each trajectory is accumulated from its own event stream into
         its slice of one [n,T,...] buffer, then ONE decode(+rectify)+crop and ONE quantile launch cover all n*T frames
-        (the per-frame work is independent). Returns (frames [T*n,1,h,w] in time-major order t*n + s, counts
-        [n,T,2,H,W], voxel [n,T,B,H,W] | None)."""
+        (the per-frame work is independent). ready: optional CUDA events, one per trajectory, that the current stream
+        waits on before touching that trajectory's records (its host-to-device copy). Returns (frames [T*n,1,h,w] in
+        time-major order t*n + s, counts [n,T,2,H,W], voxel [n,T,B,H,W] | None)."""
         lib = _lib.load()
         n = len(records_list)
         T = edges_list[0].shape[0] - 1
@@ -88,19 +89,21 @@ class PerceptionPipeline:
         counts = torch.empty((n, T, 2, self.H, self.W), dtype=torch.int32, device=self.dev)
         voxel = torch.empty((n, T, self.B, self.H, self.W), dtype=torch.float32, device=self.dev) if want_voxel else None
         for s, (rec, edges) in enumerate(zip(records_list, edges_list)):
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready[s])
             L1.accumulate_windows(rec, edges, self.H, self.W, self.B if want_voxel else None, counts=counts[s],
                                   voxel=None if voxel is None else voxel[s])
         frames = torch.empty((n, T, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
         self._normalise(counts.view(n * T, 2, self.H, self.W), frames.view(n * T, 1, self.h, self.w))
         return frames.transpose(0, 1).reshape(T * n, 1, self.h, self.w), counts, voxel
 
-    def run_trajectories(self, records_list, edges_list, want_voxel=True):
+    def run_trajectories(self, records_list, edges_list, want_voxel=True, ready=None):
         """Config 4: several independent trajectories of equal length T on one GPU. Each trajectory is accumulated
         on its own (its events are its own stream); the model then advances all of them together, frames in
         time-major order, so the recurrent scans run n_traj-wide. Fresh state. Returns (vel [n_traj,T,3], depth
         [n_traj,T,1,h,w])."""
         n = len(records_list)
-        tm = self.frames_from_trajectories(records_list, edges_list, want_voxel)[0]
+        tm = self.frames_from_trajectories(records_list, edges_list, want_voxel, ready=ready)[0]
         T = tm.shape[0] // n
         desvel = torch.full((T * n, 1), self.desvel, dtype=torch.float32, device=self.dev)
         vel, (depth, _, _) = self.model.forward_trajectories([tm, desvel, [None, None], None], n)
@@ -129,7 +132,7 @@ class TrajectoryFeeder:
         self.pipe = pipe
         self.bufs = [torch.empty((max_events, 16), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.ready = [torch.cuda.Event() for _ in range(2)]      # H2D of slot finished
+        self.ready = [[] for _ in range(2)]                      # per slot: one event per trajectory, its H2D copy finished
         self.free = [torch.cuda.Event() for _ in range(2)]       # compute on slot finished
         self.h_vel = [torch.empty((max_windows, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
@@ -142,11 +145,13 @@ class TrajectoryFeeder:
     def _stage(self, slot, recs):
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.free[slot])
+            while len(self.ready[slot]) < len(recs):
+                self.ready[slot].append(torch.cuda.Event())
             off = 0
-            for r in recs:
+            for s, r in enumerate(recs):
                 self.bufs[slot][off: off + r.shape[0]].copy_(r, non_blocking=True)
                 off += r.shape[0]
-            self.ready[slot].record(self.copy_stream)
+                self.ready[slot][s].record(self.copy_stream)      # the pipeline starts on trajectory s while s+1 is still in flight
 
     def run(self, batches):
         it = iter(batches)
@@ -164,7 +169,6 @@ class TrajectoryFeeder:
             nxt = next(it, None)
             if nxt is not None:
                 self._stage(slot ^ 1, self._as_lists(nxt)[0])          # overlaps with the compute below
-            main.wait_event(self.ready[slot])
             recs, edges = self._as_lists(cur)
             views, off = [], 0
             for r in recs:
@@ -174,9 +178,10 @@ class TrajectoryFeeder:
             with torch.no_grad():
                 self.pipe.reset()
                 if n == 1:
+                    main.wait_event(self.ready[slot][0])
                     vel = self.pipe(views[0], edges[0])[0].view(1, T, 3)
                 else:
-                    vel = self.pipe.run_trajectories(views, edges)[0]
+                    vel = self.pipe.run_trajectories(views, edges, ready=self.ready[slot][:n])[0]
                 out = self.h_vel[slot][: n * T].view(n, T, 3)
                 out.copy_(vel, non_blocking=True)
             self.free[slot].record(main)
