@@ -45,6 +45,7 @@ SIGNATURES = {
     "evfly_decode_crop": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "evfly_difflog_events_f64": (_i32, [_vp, _vp, _i64, _f64, _i32, _f64, _f64, _vp, _vp, _vp]),
     "evfly_min_cutoff_f32": (_i32, [_vp, _i64, _f32, _vp]),
+    "evfly_counts_normalise": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "evfly_remap_bicubic_f32": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "evfly_remap_events_f32": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "evfly_quantile_scale_clip": (_i32, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),

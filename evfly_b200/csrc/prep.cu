@@ -313,6 +313,107 @@ k_quantile_scale_clip(const float* x, int64_t elems, float qfrac, float lo, floa
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// decode_crop(counts) + quantile_scale_clip in one kernel for frames that come from integer counts:
+// |frame| = 0.2f * |n+ - n-| is monotonic in the integer |n+ - n-|, so the two order statistics torch.quantile
+// interpolates between are found EXACTLY from one integer histogram pass (2047 levels per pass; hotter pixels take
+// another pass with the base moved up), instead of three radix passes over a materialised fp32 frame. The arithmetic
+// of the result (fp32 rank, lerp, x / q, clip, cutoff) is the same instruction sequence as the two-kernel path, so
+// the output is bit-identical to it (tests/test_accumulate_gpu.py).
+// ---------------------------------------------------------------------------------------
+constexpr unsigned kLevels = kSelBins - 1;      // bins 0..2046 are exact levels, bin 2047 collects everything above
+
+__global__ void __launch_bounds__(kSelThreads)
+k_counts_normalise(const int* __restrict__ counts, int H, int W, int h, int w, int r0, int c0, float scale, float qfrac, float lo,
+                   float hi, float cutoff, float* __restrict__ out, float* __restrict__ qout) {
+    __shared__ unsigned s_hist[kSelBins];
+    __shared__ unsigned s_wsum[32];
+    __shared__ unsigned s_level[2];          // |n+ - n-| of the order statistics kb, ka
+    __shared__ int s_found[2];
+    __shared__ float s_q;
+    const int* neg = counts + (int64_t)blockIdx.x * 2 * H * W;
+    const int* pos = neg + (int64_t)H * W;
+    const int64_t elems = (int64_t)h * w;
+    float* of = out + (int64_t)blockIdx.x * elems;
+    const float rank = __fmul_rn(qfrac, (float)(elems - 1));
+    const float rb = floorf(rank), ra = ceilf(rank);
+    const unsigned long long kq[2] = {(unsigned long long)rb, (unsigned long long)ra};
+    const float wgt = __fsub_rn(rank, rb);
+    if (threadIdx.x < 2) s_found[threadIdx.x] = 0;
+    unsigned base = 0;
+    unsigned long long below = 0;            // elements with |d| < base
+    for (;;) {
+        for (unsigned b = threadIdx.x; b < kSelBins; b += blockDim.x) s_hist[b] = 0;
+        __syncthreads();
+        unsigned zero_bin = 0;               // most pixels of an event frame are empty: count level `base` in a register
+        for (int64_t i = threadIdx.x; i < elems; i += blockDim.x) {
+            const int row = (int)(i / w), col = (int)(i - (int64_t)row * w);
+            const int64_t src = (int64_t)(row + r0) * W + (col + c0);
+            const int d = pos[src] - neg[src];
+            const unsigned a = (unsigned)(d < 0 ? -d : d);
+            if (a >= base) {
+                const unsigned key = min(a - base, kLevels);
+                if (key == 0) ++zero_bin; else atomicAdd(&s_hist[key], 1u);
+            }
+        }
+        if (zero_bin) atomicAdd(&s_hist[0], zero_bin);
+        __syncthreads();
+        // block-wide exclusive scan, two bins per thread
+        const unsigned b0 = threadIdx.x * 2;
+        const unsigned c0v = s_hist[b0], c1v = s_hist[b0 + 1];
+        unsigned incl = c0v + c1v;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned wv = s_wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, wv, d);
+                if (lane >= d) wv += y;
+            }
+            s_wsum[lane] = wv;
+        }
+        __syncthreads();
+        const unsigned long long excl = below + (wid ? s_wsum[wid - 1] : 0u) + (incl - c0v - c1v);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (!s_found[j]) {
+                if (kq[j] >= excl && kq[j] < excl + c0v && b0 < kLevels) { s_level[j] = base + b0; s_found[j] = 1; }
+                else if (kq[j] >= excl + c0v && kq[j] < excl + c0v + c1v && b0 + 1 < kLevels) { s_level[j] = base + b0 + 1; s_found[j] = 1; }
+            }
+        }
+        const unsigned in_levels = s_wsum[31] - s_hist[kLevels];     // elements with base <= |d| < base + kLevels
+        __syncthreads();
+        if ((s_found[0] && s_found[1]) || base > (1u << 30)) break;      // (the bound only guards against garbage counts)
+        below += in_levels;
+        base += kLevels;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float vb = __fmul_rn((float)s_level[0], scale), va = __fmul_rn((float)s_level[1], scale);
+        const float diff = __fsub_rn(va, vb);      // at::lerp, as in k_quantile_scale_clip
+        const float q = (wgt < 0.5f) ? __fadd_rn(vb, __fmul_rn(wgt, diff)) : __fsub_rn(va, __fmul_rn(diff, __fsub_rn(1.0f, wgt)));
+        s_q = q;
+        if (qout) qout[blockIdx.x] = q;
+    }
+    __syncthreads();
+    const float q = s_q;
+    for (int64_t i = threadIdx.x; i < elems; i += blockDim.x) {
+        const int row = (int)(i / w), col = (int)(i - (int64_t)row * w);
+        const int64_t src = (int64_t)(row + r0) * W + (col + c0);
+        float v = __fdiv_rn(__fmul_rn((float)(pos[src] - neg[src]), scale), q);
+        if (v == v) v = fminf(fmaxf(v, lo), hi);
+        if (fabsf(v) < cutoff) v = 0.0f;
+        of[i] = v;
+    }
+}
+
 }  // namespace evfly
 
 using namespace evfly;
@@ -382,6 +483,20 @@ extern "C" int evfly_quantile_scale_clip(const float* d_x, int N, int64_t elems_
     if (N == 0) return EVFLY_OK;
     k_quantile_scale_clip<<<N, kSelThreads, 0, (cudaStream_t)stream>>>(
         d_x, elems_per_frame, qfrac, lo, hi, cutoff, d_out, d_q);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_counts_normalise(const int32_t* d_counts, int N, int H, int W, int h, int w, float scale, float qfrac, float lo,
+                                      float hi, float cutoff, float* d_out, float* d_q, void* stream) {
+    EVFLY_REQUIRE(N >= 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= H && w <= W, "counts_normalise: bad shape");
+    EVFLY_REQUIRE((h == H || h % 2 == 0) && (w == W || w % 2 == 0), "counts_normalise: crop sizes must be even");
+    EVFLY_REQUIRE((int64_t)h * w < (1ll << 24), "counts_normalise: fp32 rank arithmetic needs h*w < 2^24");
+    EVFLY_REQUIRE(qfrac >= 0.f && qfrac <= 1.f && scale > 0.f, "counts_normalise: q must be in [0,1], scale > 0");
+    EVFLY_REQUIRE(d_counts && d_out, "counts_normalise: null pointer");
+    if (N == 0) return EVFLY_OK;
+    const int r0 = (h == H) ? 0 : H / 2 - h / 2, c0 = (w == W) ? 0 : W / 2 - w / 2;
+    k_counts_normalise<<<N, kSelThreads, 0, (cudaStream_t)stream>>>(d_counts, H, W, h, w, r0, c0, scale, qfrac, lo, hi, cutoff, d_out, d_q);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

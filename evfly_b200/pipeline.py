@@ -52,8 +52,10 @@ class PerceptionPipeline:
         N = counts.shape[0]
         st = _lib.stream_ptr()
         if self.aligner is None:
-            _lib.check(lib.evfly_decode_crop(None, _lib.ptr(counts), N, self.H, self.W, self.h, self.w, 0.2,
-                                             _lib.ptr(frames), st), "evfly_decode_crop")
+            # integer counts -> normalised frame in one kernel (exact order statistics from an integer histogram)
+            _lib.check(lib.evfly_counts_normalise(_lib.ptr(counts), N, self.H, self.W, self.h, self.w, 0.2, 0.97, -1.0, 1.0, 0.0,
+                                                  _lib.ptr(frames), None, st), "evfly_counts_normalise")
+            return
         else:
             # decode at full resolution, rectify, then centre-crop; only the cropped window of the remap is computed
             # (the maps are indexed by OUTPUT pixel)

@@ -209,6 +209,13 @@ int evfly_difflog_events_f64(const double* d_im, const double* d_prev, int64_t n
  * evfly_quantile_scale_clip.                                                                       */
 int evfly_min_cutoff_f32(float* d_x, int64_t n, float cutoff, void* stream);
 
+/* evfly_decode_crop (counts form) followed by evfly_quantile_scale_clip, fused for frames that come from integer
+ * counts: out[n] = clip(0.2f*(n+ - n-) / quantile(|.|, q), lo, hi) over the centre crop, bit-identical to the two
+ * calls. The order statistics are found exactly from one integer histogram of |n+ - n-| (run.py:334-336,345-351,
+ * 250-253; learner/dataloading.py:515-524). d_q (optional): the N quantiles.                              */
+int evfly_counts_normalise(const int32_t* d_counts, int N, int H, int W, int h, int w, float scale, float qfrac,
+                           float lo, float hi, float cutoff, float* d_out, float* d_q, void* stream);
+
 /* ---- next row N3: rectification (utils/calibration_tools/rectify_bag.py:91-138; evfly_ros/run.py:339-340) ----
  * dst[n][i][j] = cv2.remap(src[n], mapx, mapy, INTER_CUBIC) (constant-0 border), bit for bit: coordinates rounded
  * half-even to 1/32 pixel, A = -0.75 cubic table, OpenCV's summation order, no FMA. src: float32 [N,H,W], or with

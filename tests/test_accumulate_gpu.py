@@ -279,3 +279,35 @@ def test_accumulate_counts_binned_bucket_overflow_is_exact(cuda_lib):
     a = L1.accumulate_counts(d, H, W, algo="red")
     b = L1.accumulate_counts(d, H, W, algo="binned")
     assert torch.equal(a, b) and int(a.sum()) == n
+
+
+# ---- fused counts -> normalised frame == decode_crop + quantile_scale_clip, bit for bit -----------------
+@pytest.mark.parametrize("case", ["sparse", "dense", "hot", "empty", "tiny"])
+def test_counts_normalise_equals_two_step_path(cuda_lib, case):
+    rng = np.random.default_rng(abs(hash(case)) % 1000)
+    N, H, W, h, w = 5, 480, 640, 260, 346
+    if case == "tiny":
+        N, H, W, h, w = 3, 12, 16, 8, 10
+    lam = {"sparse": 0.05, "dense": 3.0, "hot": 0.3, "empty": 0.0, "tiny": 1.0}[case]
+    counts = rng.poisson(lam, (N, 2, H, W)).astype(np.int32)
+    if case == "hot":       # more than 3 % of the pixels above 2047 events: the quantile lies in the overflow bin -> second pass
+        m = rng.random((N, H, W)) < 0.08
+        counts[:, 1][m] += rng.integers(2047, 9000, int(m.sum())).astype(np.int32)
+    if case == "empty":
+        counts[0, 1, H // 2, W // 2] = 3      # one frame with a single event, the others all zero (quantile 0 -> NaN rule)
+    d = torch.from_numpy(counts).cuda()
+    ref = torch.empty((N, 1, h, w), dtype=torch.float32, device="cuda")
+    qref = torch.empty((N,), dtype=torch.float32, device="cuda")
+    st = _lib.stream_ptr()
+    _lib.check(cuda_lib.evfly_decode_crop(None, _lib.ptr(d), N, H, W, h, w, 0.2, _lib.ptr(ref), st))
+    _lib.check(cuda_lib.evfly_quantile_scale_clip(_lib.ptr(ref), N, h * w, 0.97, -1.0, 1.0, 0.0, _lib.ptr(ref), _lib.ptr(qref), st))
+    got = torch.empty_like(ref)
+    qgot = torch.empty_like(qref)
+    _lib.check(cuda_lib.evfly_counts_normalise(_lib.ptr(d), N, H, W, h, w, 0.2, 0.97, -1.0, 1.0, 0.0, _lib.ptr(got), _lib.ptr(qgot), st))
+    assert np.array_equal(qgot.cpu().numpy(), qref.cpu().numpy())
+    assert np.array_equal(got.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+    # and against the oracle chain
+    r0, c0 = H // 2 - h // 2, W // 2 - w // 2
+    fr = (0.2 * (counts[:, 1].astype(np.float32) - counts[:, 0].astype(np.float32))).astype(np.float32)[:, None, r0:r0 + h, c0:c0 + w]
+    want, _ = O.quantile_scale_clip(np.ascontiguousarray(fr), 0.97, -1.0, 1.0)
+    assert np.array_equal(got.cpu().numpy(), want, equal_nan=True)
