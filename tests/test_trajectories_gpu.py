@@ -61,3 +61,30 @@ def test_pipeline_run_trajectories(cuda_lib):
             pipe.reset()
             v, d, _, _ = pipe(recs[s], edges[s])
             np.testing.assert_allclose(vel[s].cpu().numpy(), v.cpu().numpy(), rtol=2e-2, atol=2e-3)
+
+
+def test_prefetched_two_stage_execution_equals_run_trajectories(cuda_lib):
+    """L1+L2 on the side stream (prefetch_trajectories) + model on the main stream (run_prefetched), with the next
+    batch prefetched before the current model runs, gives exactly what run_trajectories gives batch by batch."""
+    with torch.no_grad():
+        m = build_deployed_model("cpu")
+        m.load_state_dict(synth_state_dict(shapes_of(m), 31))
+        m = evfly_b200.set_precision(m.cuda().eval(), "bf16")
+        pipe = PerceptionPipeline(m, sensor_hw=(260, 346))
+        batches = []
+        for b in range(3):
+            recs, edges = [], []
+            for s in range(2):
+                r, e = synthetic_stream(70 + 10 * b + s, 4, 50_000, 260, 346)
+                recs.append(to_device(r)); edges.append(torch.from_numpy(e).cuda())
+            batches.append((recs, edges))
+        want = [tuple(t.clone() for t in pipe.run_trajectories(*b)) for b in batches]
+        got = []
+        h = pipe.prefetch_trajectories(*batches[0])
+        for i in range(len(batches)):
+            h_next = pipe.prefetch_trajectories(*batches[i + 1]) if i + 1 < len(batches) else None
+            got.append(tuple(t.clone() for t in pipe.run_prefetched(h)))
+            h = h_next
+        torch.cuda.synchronize()
+        for (v0, d0), (v1, d1) in zip(want, got):
+            assert torch.equal(v0, v1) and torch.equal(d0, d1)
