@@ -315,7 +315,7 @@ class PipelineWorkload:
             "achieved": self.acc_bytes / (acc_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": self.acc_bytes / (acc_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": self.acc_bytes, "ms": acc_ms}],
             "tc_kernel_ms_per_step": tc_ms / n_steps}
-        return {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv kernels: k_tc_conv3x3_halo (Cin,Cout<=64 layers) + k_tc_conv_bf16 (other 3x3, 1x1, transposed convs, fused ConvLSTM steps, ViT Linear layers)",
+        return {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv kernels: k_tc_conv3x3_halo (Cin,Cout<=64 layers, resident weights) + k_tc_conv3x3_halo_ws (Cin=128 layers, streamed weights) + k_tc_conv_bf16 (other 3x3, 1x1, transposed convs, persistent ConvLSTM scan, ViT Linear layers)",
                 "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
                 "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
                 "algorithmic_flops_per_launch": self.tc_flops / launches, "launches_per_step": launches,
