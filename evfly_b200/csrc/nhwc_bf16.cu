@@ -96,21 +96,25 @@ __device__ __forceinline__ void bilin_src(int dst, int in, int out, int& i0, int
     l1 = src - (float)i0;
 }
 
+template <typename Idx>
 __global__ void __launch_bounds__(256)
 k_resize_bilinear_nhwc(const uint4* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int Hp, int Wp, int vh, int vw,
                        int C8, int OH, int OW, long long out_ld, int out_c0) {
-    const long long total = (long long)N * OH * OW * C8;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int c = (int)(i % C8);
-        const long long pix = i / C8;
-        const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH);
-        const long long n = pix / ((long long)OW * OH);
+    // Idx = unsigned when the element count fits 32 bits: 64-bit integer division costs ~100 instructions
+    const Idx total = (Idx)N * (Idx)OH * (Idx)OW * (Idx)C8;
+    const Idx stride = (Idx)gridDim.x * blockDim.x;
+    for (Idx i = (Idx)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const Idx pix = i / (Idx)C8;
+        const int c = (int)(i - pix * (Idx)C8);
+        const Idx prow = pix / (Idx)OW;
+        const int ow = (int)(pix - prow * (Idx)OW);
+        const Idx n = prow / (Idx)OH;
+        const int oh = (int)(prow - n * (Idx)OH);
         int h0, h1, w0, w1;
         float lh, lw;
         bilin_src(oh, vh, OH, h0, h1, lh);
         bilin_src(ow, vw, OW, w0, w1, lw);
-        const uint4* base = x + n * (long long)Hp * Wp * C8 + c;
+        const uint4* base = x + (long long)n * Hp * Wp * C8 + c;
         const uint4 v00 = base[((long long)h0 * Wp + w0) * C8], v01 = base[((long long)h0 * Wp + w1) * C8];
         const uint4 v10 = base[((long long)h1 * Wp + w0) * C8], v11 = base[((long long)h1 * Wp + w1) * C8];
         const uint32_t* a = &v00.x; const uint32_t* b = &v01.x; const uint32_t* d = &v10.x; const uint32_t* e = &v11.x;
@@ -123,7 +127,7 @@ k_resize_bilinear_nhwc(const uint4* __restrict__ x, __nv_bfloat16* __restrict__ 
             const float r1 = (1.f - lh) * ((1.f - lw) * fa.y + lw * fb.y) + lh * ((1.f - lw) * fd.y + lw * fe.y);
             po[q] = pack_bf16x2(r0, r1);
         }
-        *reinterpret_cast<uint4*>(y + pix * out_ld + out_c0 + c * 8) = o;
+        *reinterpret_cast<uint4*>(y + (long long)pix * out_ld + out_c0 + c * 8) = o;
     }
 }
 
@@ -215,8 +219,13 @@ extern "C" int evfly_resize_bilinear_nhwc_bf16(const void* d_x, void* d_y, int N
     EVFLY_REQUIRE(d_x && d_y && N >= 0 && C % 8 == 0 && vh > 0 && vw > 0 && vh <= Hp && vw <= Wp && OH > 0 && OW > 0 && out_ld % 8 == 0 && out_c0 % 8 == 0,
                   "resize_bilinear_nhwc_bf16: bad argument");
     if (N == 0) return EVFLY_OK;
-    k_resize_bilinear_nhwc<<<g_ew((long long)N * OH * OW * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4*>(d_x), reinterpret_cast<__nv_bfloat16*>(d_y), N, Hp, Wp, vh, vw, C / 8, OH, OW, out_ld, out_c0);
+    const long long total = (long long)N * OH * OW * (C / 8);
+    if (total < (1ll << 31))
+        k_resize_bilinear_nhwc<unsigned><<<g_ew(total), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(d_x), reinterpret_cast<__nv_bfloat16*>(d_y), N, Hp, Wp, vh, vw, C / 8, OH, OW, out_ld, out_c0);
+    else
+        k_resize_bilinear_nhwc<long long><<<g_ew(total), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(d_x), reinterpret_cast<__nv_bfloat16*>(d_y), N, Hp, Wp, vh, vw, C / 8, OH, OW, out_ld, out_c0);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

@@ -267,35 +267,63 @@ __device__ __forceinline__ void bilinear_src(int dst, int in, int out, bool alig
     l1 = src - (float)i0;
 }
 
+// One thread per 4 consecutive output pixels of a row: the row decomposition (three divisions) and the vertical
+// source rows / weight are computed once per 4 outputs, in 32-bit arithmetic when the problem allows (64-bit integer
+// division costs ~100 instructions on the GPU and used to dominate this kernel).
+template <typename Idx>
 __global__ void __launch_bounds__(256)
 k_resize_bilinear(const float* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W, int OH,
                   int OW, int align, Strides4 xs, Strides4 ys, float mul, float add, float lo, float hi,
                   int pre, float pre_mul, float pre_lo, float pre_hi) {
-    const long long total = (long long)N * C * OH * OW;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int ow = (int)(i % OW), oh = (int)((i / OW) % OH);
-        const int c = (int)((i / ((long long)OW * OH)) % C);
-        const long long n = i / ((long long)OW * OH * C);
-        int h0, h1, w0, w1;
-        float lh, lw;
+    const Idx OWQ = (Idx)((OW + 3) >> 2);
+    const Idx total = (Idx)N * (Idx)C * (Idx)OH * OWQ;
+    const Idx stride = (Idx)gridDim.x * blockDim.x;
+    for (Idx i = (Idx)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const Idx rowi = i / OWQ;
+        const int owq = (int)(i - rowi * OWQ);
+        const Idx nc = rowi / (Idx)OH;
+        const int oh = (int)(rowi - nc * (Idx)OH);
+        const Idx n = nc / (Idx)C;
+        const int c = (int)(nc - n * (Idx)C);
+        int h0, h1;
+        float lh;
         bilinear_src(oh, H, OH, align, h0, h1, lh);
-        bilinear_src(ow, W, OW, align, w0, w1, lw);
-        const float* p = x + n * xs.s[0] + c * xs.s[1];
-        float v00 = p[h0 * xs.s[2] + w0 * xs.s[3]], v01 = p[h0 * xs.s[2] + w1 * xs.s[3]];
-        float v10 = p[h1 * xs.s[2] + w0 * xs.s[3]], v11 = p[h1 * xs.s[2] + w1 * xs.s[3]];
-        if (pre) {      // the source is seen through clip(v * pre_mul, pre_lo, pre_hi) (NaN kept), without materialising it
-            v00 *= pre_mul; v01 *= pre_mul; v10 *= pre_mul; v11 *= pre_mul;
-            if (v00 == v00) v00 = fminf(fmaxf(v00, pre_lo), pre_hi);
-            if (v01 == v01) v01 = fminf(fmaxf(v01, pre_lo), pre_hi);
-            if (v10 == v10) v10 = fminf(fmaxf(v10, pre_lo), pre_hi);
-            if (v11 == v11) v11 = fminf(fmaxf(v11, pre_lo), pre_hi);
+        const float* p = x + (long long)n * xs.s[0] + (long long)c * xs.s[1];
+        const float* r0 = p + (long long)h0 * xs.s[2];
+        const float* r1 = p + (long long)h1 * xs.s[2];
+        float* yo = y + (long long)n * ys.s[0] + (long long)c * ys.s[1] + (long long)oh * ys.s[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ow = owq * 4 + k;
+            if (ow >= OW) break;
+            int w0, w1;
+            float lw;
+            bilinear_src(ow, W, OW, align, w0, w1, lw);
+            float v00 = r0[w0 * xs.s[3]], v01 = r0[w1 * xs.s[3]];
+            float v10 = r1[w0 * xs.s[3]], v11 = r1[w1 * xs.s[3]];
+            if (pre) {      // the source is seen through clip(v * pre_mul, pre_lo, pre_hi) (NaN kept), without materialising it
+                v00 *= pre_mul; v01 *= pre_mul; v10 *= pre_mul; v11 *= pre_mul;
+                if (v00 == v00) v00 = fminf(fmaxf(v00, pre_lo), pre_hi);
+                if (v01 == v01) v01 = fminf(fmaxf(v01, pre_lo), pre_hi);
+                if (v10 == v10) v10 = fminf(fmaxf(v10, pre_lo), pre_hi);
+                if (v11 == v11) v11 = fminf(fmaxf(v11, pre_lo), pre_hi);
+            }
+            float v = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+            v = v * mul + add;
+            if (v == v) v = fminf(fmaxf(v, lo), hi);
+            yo[ow * ys.s[3]] = v;
         }
-        float v = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
-        v = v * mul + add;
-        if (v == v) v = fminf(fmaxf(v, lo), hi);
-        y[n * ys.s[0] + c * ys.s[1] + oh * ys.s[2] + ow * ys.s[3]] = v;
     }
+}
+
+static void launch_resize_bilinear(const float* d_x, float* d_y, int N, int C, int H, int W, int OH, int OW, int align, Strides4 xs, Strides4 ys,
+                                   float mul, float add, float lo, float hi, int pre, float pre_mul, float pre_lo, float pre_hi, cudaStream_t st) {
+    const long long items = (long long)N * C * OH * ((OW + 3) / 4);
+    const int grid = stream_grid(items, 256, 32);
+    if (items < (1ll << 31))
+        k_resize_bilinear<unsigned><<<grid, 256, 0, st>>>(d_x, d_y, N, C, H, W, OH, OW, align, xs, ys, mul, add, lo, hi, pre, pre_mul, pre_lo, pre_hi);
+    else
+        k_resize_bilinear<long long><<<grid, 256, 0, st>>>(d_x, d_y, N, C, H, W, OH, OW, align, xs, ys, mul, add, lo, hi, pre, pre_mul, pre_lo, pre_hi);
 }
 
 // one warp per row
@@ -595,8 +623,8 @@ extern "C" int evfly_resize_bilinear_f32(const float* d_x, const int64_t* xs, fl
                                          float mul, float add, float lo, float hi, void* stream) {
     EVFLY_REQUIRE(d_x && d_y && xs && ys && N >= 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "resize_bilinear_f32: bad argument");
     if (N == 0) return EVFLY_OK;
-    k_resize_bilinear<<<ew_grid((long long)N * C * OH * OW), 256, 0, (cudaStream_t)stream>>>(
-        d_x, d_y, N, C, H, W, OH, OW, align_corners, to_strides(xs), to_strides(ys), mul, add, lo, hi, 0, 1.f, 0.f, 0.f);
+    launch_resize_bilinear(d_x, d_y, N, C, H, W, OH, OW, align_corners, to_strides(xs), to_strides(ys), mul, add, lo, hi, 0, 1.f, 0.f, 0.f,
+                           (cudaStream_t)stream);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }
@@ -605,8 +633,8 @@ extern "C" int evfly_resize_bilinear_premap_f32(const float* d_x, const int64_t*
                                                int OH, int OW, int align_corners, float pre_mul, float pre_lo, float pre_hi, void* stream) {
     EVFLY_REQUIRE(d_x && d_y && xs && ys && N >= 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "resize_bilinear_premap_f32: bad argument");
     if (N == 0) return EVFLY_OK;
-    k_resize_bilinear<<<ew_grid((long long)N * C * OH * OW), 256, 0, (cudaStream_t)stream>>>(
-        d_x, d_y, N, C, H, W, OH, OW, align_corners, to_strides(xs), to_strides(ys), 1.f, 0.f, -INFINITY, INFINITY, 1, pre_mul, pre_lo, pre_hi);
+    launch_resize_bilinear(d_x, d_y, N, C, H, W, OH, OW, align_corners, to_strides(xs), to_strides(ys), 1.f, 0.f, -INFINITY, INFINITY, 1, pre_mul,
+                           pre_lo, pre_hi, (cudaStream_t)stream);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

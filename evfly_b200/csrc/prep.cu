@@ -346,9 +346,9 @@ k_counts_normalise(const int* __restrict__ counts, int H, int W, int h, int w, i
         for (unsigned b = threadIdx.x; b < kSelBins; b += blockDim.x) s_hist[b] = 0;
         __syncthreads();
         unsigned zero_bin = 0;               // most pixels of an event frame are empty: count level `base` in a register
-        for (int64_t i = threadIdx.x; i < elems; i += blockDim.x) {
-            const int row = (int)(i / w), col = (int)(i - (int64_t)row * w);
-            const int64_t src = (int64_t)(row + r0) * W + (col + c0);
+        for (int i = threadIdx.x; i < (int)elems; i += blockDim.x) {      // 32-bit index math (elems < 2^24): 64-bit division is ~100 instructions
+            const int row = i / w, col = i - row * w;
+            const int src = (row + r0) * W + (col + c0);
             const int d = pos[src] - neg[src];
             const unsigned a = (unsigned)(d < 0 ? -d : d);
             if (a >= base) {
@@ -404,9 +404,9 @@ k_counts_normalise(const int* __restrict__ counts, int H, int W, int h, int w, i
     }
     __syncthreads();
     const float q = s_q;
-    for (int64_t i = threadIdx.x; i < elems; i += blockDim.x) {
-        const int row = (int)(i / w), col = (int)(i - (int64_t)row * w);
-        const int64_t src = (int64_t)(row + r0) * W + (col + c0);
+    for (int i = threadIdx.x; i < (int)elems; i += blockDim.x) {
+        const int row = i / w, col = i - row * w;
+        const int src = (row + r0) * W + (col + c0);
         float v = __fdiv_rn(__fmul_rn((float)(pos[src] - neg[src]), scale), q);
         if (v == v) v = fminf(fmaxf(v, lo), hi);
         if (fabsf(v) < cutoff) v = 0.0f;
@@ -491,7 +491,7 @@ extern "C" int evfly_counts_normalise(const int32_t* d_counts, int N, int H, int
                                       float hi, float cutoff, float* d_out, float* d_q, void* stream) {
     EVFLY_REQUIRE(N >= 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= H && w <= W, "counts_normalise: bad shape");
     EVFLY_REQUIRE((h == H || h % 2 == 0) && (w == W || w % 2 == 0), "counts_normalise: crop sizes must be even");
-    EVFLY_REQUIRE((int64_t)h * w < (1ll << 24), "counts_normalise: fp32 rank arithmetic needs h*w < 2^24");
+    EVFLY_REQUIRE((int64_t)h * w < (1ll << 24) && (int64_t)H * W < (1ll << 31), "counts_normalise: fp32 rank arithmetic needs h*w < 2^24 (and H*W < 2^31)");
     EVFLY_REQUIRE(qfrac >= 0.f && qfrac <= 1.f && scale > 0.f, "counts_normalise: q must be in [0,1], scale > 0");
     EVFLY_REQUIRE(d_counts && d_out, "counts_normalise: null pointer");
     if (N == 0) return EVFLY_OK;
