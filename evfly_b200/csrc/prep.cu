@@ -340,9 +340,12 @@ k_counts_normalise(const int* __restrict__ counts, int H, int W, int h, int w, i
     const unsigned long long kq[2] = {(unsigned long long)rb, (unsigned long long)ra};
     const float wgt = __fsub_rn(rank, rb);
     if (threadIdx.x < 2) s_found[threadIdx.x] = 0;
+    __syncthreads();
     unsigned base = 0;
     unsigned long long below = 0;            // elements with |d| < base
     for (;;) {
+        // which ranks earlier passes already resolved: read here, a barrier away from this pass's writes below
+        const bool fnd[2] = {s_found[0] != 0, s_found[1] != 0};
         for (unsigned b = threadIdx.x; b < kSelBins; b += blockDim.x) s_hist[b] = 0;
         __syncthreads();
         unsigned zero_bin = 0;               // most pixels of an event frame are empty: count level `base` in a register
@@ -383,7 +386,7 @@ k_counts_normalise(const int* __restrict__ counts, int H, int W, int h, int w, i
         const unsigned long long excl = below + (wid ? s_wsum[wid - 1] : 0u) + (incl - c0v - c1v);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            if (!s_found[j]) {
+            if (!fnd[j]) {
                 if (kq[j] >= excl && kq[j] < excl + c0v && b0 < kLevels) { s_level[j] = base + b0; s_found[j] = 1; }
                 else if (kq[j] >= excl + c0v && kq[j] < excl + c0v + c1v && b0 + 1 < kLevels) { s_level[j] = base + b0 + 1; s_found[j] = 1; }
             }
