@@ -59,3 +59,30 @@ def test_no_cpu_fallback_in_product_package():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_new_entry_points_validate_arguments_before_touching_the_gpu(lib):
+    """Argument errors of the rows added late in the round (no GPU needed: validation precedes every CUDA call)."""
+    rc = lib.evfly_counts_normalise(None, 4, 480, 640, 260, 346, 0.2, 0.97, -1.0, 1.0, 0.0, None, None, None)
+    assert rc == -1 and b"null" in lib.evfly_last_error()
+    rc = lib.evfly_counts_normalise(None, 4, 480, 640, 261, 346, 0.2, 0.97, -1.0, 1.0, 0.0, None, None, None)
+    assert rc == -1 and b"even" in lib.evfly_last_error()
+    rc = lib.evfly_remap_bicubic_f32(None, 0, 1, 480, 640, None, None, 640, 260, 346, 0, 0, None, None)
+    assert rc == -1 and b"remap_bicubic_f32" in lib.evfly_last_error()
+    rc = lib.evfly_tc_conv3x3_halo_bf16(None, None, None, None, 1, 20, 20, 20, 20, 48, 48, 1, None)
+    assert rc == -1
+    assert lib.evfly_accumulate_counts_binned_workspace_bytes(10_000_000, 480, 640) > 256 * 1024
+    assert lib.evfly_accumulate_counts_binned_workspace_bytes(-1, 480, 640) == 0
+
+
+def test_host_mirrors_refuse_cpu_tensors():
+    """calibration_tools / pipeline run on the device only; a CPU tensor is an error, never a silent CPU path."""
+    import numpy as np
+    import torch
+    from evfly_b200 import calibration_tools as CT
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    with pytest.raises((_lib.EvflyError, AssertionError, RuntimeError)):
+        CT.remap_bicubic(torch.zeros(1, 8, 8), torch.zeros(8, 8), torch.zeros(8, 8))
+    with pytest.raises((_lib.EvflyError, AssertionError, RuntimeError)):
+        CT.remap_img(np.zeros((8, 8), np.float32), (np.zeros((8, 8), np.float32), np.zeros((8, 8), np.float32)), False, False)
