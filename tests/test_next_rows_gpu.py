@@ -48,3 +48,19 @@ def test_resize_trajectory_matches_torch_interpolate(cuda_lib):
         got = resize_trajectory(x.numpy(), size).cpu()
         assert got.shape == want.shape
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)        # fp32 path tolerance (north_star)
+
+
+def test_dataloading_matches_reference_dataloader_golden(cuda_lib, golden_dir):
+    """normalize_event_frames / resize_trajectory against what the REFERENCE dataloader (learner/dataloading.py run on a
+    synthetic folder dataset, tests/golden/make_golden_dataloading.py) returned."""
+    import os
+    import numpy as np
+    from evfly_b200.dataloading import normalize_event_frames, resize_trajectory
+    G = np.load(os.path.join(golden_dir, "dataloading_golden.npz"))
+    modes = {"q97": (-1.0, None), "q97_cut": (-1.0, 0.05), "div2_cut": (2.0, 0.05), "raw": (0.0, None)}
+    for k in range(2):
+        for mode, (rescale, cutoff) in modes.items():
+            got = normalize_event_frames(G[f"native_in{k}"], rescale, cutoff).cpu().numpy()
+            assert np.array_equal(got, G[f"native_{mode}_out{k}"], equal_nan=True), (k, mode)      # bit-exact incl. the NaN frame
+        got = resize_trajectory(G[f"resized_in{k}"], (60, 90)).cpu().numpy()
+        np.testing.assert_allclose(got, G[f"resized_raw_out{k}"], rtol=1e-5, atol=1e-6)             # fp32 path tolerance

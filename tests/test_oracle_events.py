@@ -197,3 +197,21 @@ def test_remap_oracle_matches_cv2_bit_for_bit():
         assert np.array_equal(O.remap_bicubic(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_CUBIC))
         assert np.array_equal(O.remap_img(src, (mx, my), True, True),
                               cv2.rotate(cv2.remap(np.ascontiguousarray(src[:, ::-1]), mx, my, cv2.INTER_CUBIC), cv2.ROTATE_180))
+
+
+# ---- rows N1 / N4: the oracle vs what the REFERENCE dataloader returned for a synthetic folder dataset -----
+def test_normalisation_oracle_matches_reference_dataloader_golden(golden_dir):
+    G = np.load(os.path.join(golden_dir, "dataloading_golden.npz"))
+    modes = {"q97": (-1.0, None), "q97_cut": (-1.0, 0.05), "div2_cut": (2.0, 0.05), "raw": (0.0, None)}
+    for k in range(2):
+        x = G[f"native_in{k}"]
+        for mode, (rescale, cutoff) in modes.items():
+            got = O.normalize_event_frames(x, rescale, cutoff)
+            assert np.array_equal(got, G[f"native_{mode}_out{k}"], equal_nan=True), (k, mode)
+        # resize_input step (dataloading.py:401-416) followed by the normalisation
+        xr = torch.nn.functional.interpolate(torch.from_numpy(G[f"resized_in{k}"]).unsqueeze(1), size=(60, 90), mode="bilinear",
+                                             align_corners=False).squeeze().numpy()
+        assert np.array_equal(xr, G[f"resized_raw_out{k}"])
+        assert np.array_equal(O.normalize_event_frames(xr, -1.0, 0.05), G[f"resized_q97_cut_out{k}"], equal_nan=True)
+    assert G["native_desvel"].tolist() == [4.0, 4.0, 4.0, 5.0, 5.0, 5.0] and G["native_lengths"].tolist() == [3, 3]
+    assert np.isnan(G["native_q97_out0"][0]).all()        # the all-zero frame: quantile 0 -> 0/0 (reference behaviour F8b)
