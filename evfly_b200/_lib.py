@@ -111,7 +111,6 @@ SIGNATURES.update({
     "evfly_tc_conv3x3_same_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_shuffle_upsample_cat_bf16": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
     "evfly_tc_conv3x3_halo_pool_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "evfly_tc_shift_probe": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "evfly_lstm_seq_smemw": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
 })
 

@@ -497,12 +497,6 @@ int evfly_tc_conv3x3_same_bf16(const void* d_x, const void* d_w, const float* d_
 int evfly_shuffle_upsample_cat_bf16(const void* d_t2, int H2, int W2, int C2, const void* d_t1, int H1, int W1,
                                     int C1, void* d_out, int64_t B, int ld, void* stream);
 
-/* Hardware probe (diagnostic): D = x[shift : shift+128] @ w^T computed by tcgen05.mma from ONE TMA-loaded
- * [136, KC] tile whose descriptor starts `shift` rows into the swizzle atom (base-offset field set when
- * use_base_offset). x bf16 [136,KC], w bf16 [32,KC], out fp32 [128,32]. KC in {32 (64B swizzle), 64 (128B)}. */
-int evfly_tc_shift_probe(const void* d_x, const void* d_w, float* d_out, int KC, int shift,
-                         int use_base_offset, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -1,4 +1,4 @@
-// tc_probe.cu -- hardware probe for ONE assumption the halo-reuse convolution relies on: a UMMA
+// tc_probe.cu (TEST-ONLY library tests/native/libevfly_tc_probe.so, not part of the product ABI) -- hardware probe for ONE assumption the halo-reuse convolution relies on: a UMMA
 // shared-memory descriptor may start at a row that is NOT aligned to the swizzle atom (8 rows) when
 // its base-offset field is set to (start_address >> 7) & 7, so that a tile TMA wrote once can be
 // read by tcgen05.mma at a shift of 1 or 2 rows (the kw taps of a 3x3 conv). The probe loads

@@ -1,6 +1,8 @@
 """GPU: the tcgen05/TMEM/TMA implicit-GEMM kernel and the NHWC glue kernels of the bf16 path,
 against PyTorch on the CPU evaluated on the SAME bf16-rounded operands (fp64 accumulate), so the
 only differences are fp32 accumulation order and the final bf16 rounding of the output."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -202,12 +204,17 @@ def test_fused_convlstm_step(cuda_lib):
 def test_shifted_descriptor_probe(cuda_lib):
     """The hardware assumption of the halo-reuse conv: a UMMA descriptor may start at any row of a TMA-written
     swizzled tile (base_offset = 0, swizzle on absolute address bits)."""
+    import ctypes
     from evfly_b200 import _lib
+    probe_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "libevfly_tc_probe.so")
+    assert os.path.exists(probe_path), "tests/native/libevfly_tc_probe.so is built by __graft_entry__.build()"
+    probe = ctypes.CDLL(probe_path).evfly_tc_shift_probe
+    probe.restype, probe.argtypes = ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
     for KC in (32, 64):
         x, w = rnd(136, KC, seed=1).to(BF).cuda(), rnd(32, KC, seed=2).to(BF).cuda()
         for shift in (0, 1, 2, 5, 8):
             out = torch.empty((128, 32), device="cuda")
-            _lib.check(cuda_lib.evfly_tc_shift_probe(x.data_ptr(), w.data_ptr(), out.data_ptr(), KC, shift, 0, _lib.stream_ptr()))
+            _lib.check(probe(x.data_ptr(), w.data_ptr(), out.data_ptr(), KC, shift, 0, _lib.stream_ptr()))
             want = x[shift:shift + 128].float() @ w.float().t()
             assert torch.allclose(out, want, rtol=1e-4, atol=1e-4), (KC, shift)
 
