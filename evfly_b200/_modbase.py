@@ -41,10 +41,21 @@ class PackedModule(nn.Module):
         return p.device
 
     def _check_inference(self):
-        if self.training and torch.is_grad_enabled():
+        """Forward-only, eval-folded kernels (Dropout off, BatchNorm running statistics folded into the conv, spectral
+        norm without power iteration): a module left in train() mode would silently diverge from the reference, which
+        uses train-mode semantics there, so that is refused whatever the grad mode; with eval() and grad enabled the
+        outputs carry no autograd graph, which a fine-tuning loop must be told about."""
+        if self.training:
             raise _lib.EvflyError(
-                f"{type(self).__name__}: forward-only kernels. Call .eval() and run under torch.no_grad(), as every "
+                f"{type(self).__name__}: forward-only inference kernels with eval-mode semantics. Call .eval() first, as every "
                 "inference call site of the reference does (run.py:261, run_competition.py:535, learner.py:755).")
+        if torch.is_grad_enabled() and not PackedModule._warned_grad:
+            PackedModule._warned_grad = True
+            import warnings
+            warnings.warn(f"{type(self).__name__}: evfly_b200 kernels are forward-only; outputs carry no autograd graph. "
+                          "Run inference under torch.no_grad() (training through these modules is not supported).", stacklevel=3)
+
+    _warned_grad = False
 
 
 def to_dev(t, device):

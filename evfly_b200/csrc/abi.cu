@@ -18,6 +18,18 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int device_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = cache[dev & 63].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
+        cache[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 }  // namespace evfly
 
 extern "C" int evfly_abi_version(void) { return EVFLY_ABI_VERSION; }

@@ -372,6 +372,13 @@ k_u8_saturate_replay(const uint4* __restrict__ ev, int64_t n, unsigned H, unsign
     }
 }
 
+// used by accumulate_tiled.cu (kernels cannot be launched across translation units without -rdc)
+int launch_window_ranges(const void* ev, int64_t n, const int64_t* edges, int T, int64_t* ranges, cudaStream_t st) {
+    k_window_ranges<<<(T + 1 + 3) / 4, 128, 0, st>>>(reinterpret_cast<const uint4*>(ev), n, edges, T, ranges);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
 }  // namespace evfly
 
 // =========================================================================================

@@ -207,11 +207,7 @@ extern "C" int evfly_accumulate_counts_binned(const evfly_event* d_events, int64
     unsigned short* buckets = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(d_ws) + kCursorBytes);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)n_tiles * 16 + (size_t)kChunk * 8;
-    static bool attr = false;
-    if (!attr) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_bin_events, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
-    }
+    EVFLY_SMEM_ATTR(100 * 1024, k_bin_events);
     const int grid = stream_grid(n, kChunk, 6);
     k_bin_events<<<grid, 256, smem, st>>>(reinterpret_cast<const uint4*>(d_events), n, (unsigned)H, (unsigned)W, n_tiles, cap, cursors, buckets, d_counts);
     EVFLY_LAUNCHED();

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 #include "../../include/evfly_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -64,6 +65,30 @@ __device__ __forceinline__ float4 ld_stream_f4(const void* p) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 #endif
+
+// One-time setup that belongs to a DEVICE's context (cudaFuncSetAttribute): done once per device and call site, so a
+// process that drives several GPUs configures every one of them (a function-local `static bool` configured
+// only the first device and the kernels of the second failed to launch with > 48 KB of shared memory).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0ull};
+    unsigned long long bit() const {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return 1ull << (dev & 63);
+    }
+};
+#define EVFLY_SMEM_ATTR(bytes, ...)                                                                                   \
+    do {                                                                                                               \
+        static evfly::PerDeviceOnce once__;                                                                            \
+        const unsigned long long bit__ = once__.bit();                                                                 \
+        if (!(once__.mask.load(std::memory_order_acquire) & bit__)) {                                                  \
+            EVFLY_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+            once__.mask.fetch_or(bit__, std::memory_order_release);                                                    \
+        }                                                                                                              \
+    } while (0)
+
+// number of SMs of the CURRENT device (cached per device); persistent kernels with a grid barrier size their grid from it
+int device_sm_count();
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -592,11 +592,7 @@ extern "C" int evfly_linear_smallm_f32(const float* d_x, int64_t x_ld, const flo
     EVFLY_REQUIRE(d_x && d_w && d_y && M > 0 && M <= kSmallM && N > 0 && K > 0 && (size_t)M * K * 4 <= 160 * 1024, "linear_smallm_f32: bad argument (M <= 8)");
     EVFLY_REQUIRE(act >= 0 && act <= EVFLY_ACT_SIGMOID, "linear_smallm_f32: bad activation");
     const size_t smem = (size_t)M * K * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_linear_smallm, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr = true;
-    }
+    EVFLY_SMEM_ATTR(160 * 1024, k_linear_smallm);
     k_linear_smallm<<<(unsigned)ceil_div(N, 8), 256, smem, (cudaStream_t)stream>>>(d_x, x_ld, d_w, d_bias, d_res, res_ld, d_y, y_ld, M, N, K, act);
     EVFLY_LAUNCHED();
     return EVFLY_OK;

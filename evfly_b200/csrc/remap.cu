@@ -10,7 +10,9 @@
 
 namespace evfly {
 
-__constant__ float c_cubic[32 * 4];
+// OpenCV's bicubic coefficient table travels as a kernel argument (constant bank): a __constant__ symbol would exist
+// once per device and need an upload per device, which is illegal inside a CUDA-graph capture
+struct CubicTab { float v[32 * 4]; };
 
 static void cubic_table_host(float* tab) {
     const float A = -0.75f;
@@ -36,7 +38,7 @@ __device__ __forceinline__ float src_at(const void* img, int W, int y, int x, in
 template <bool U8>
 __global__ void __launch_bounds__(256)
 k_remap_bicubic(const void* __restrict__ src, int N, int H, int W, const float* __restrict__ mapx, const float* __restrict__ mapy,
-                long long map_ld, int OH, int OW, int flip, int rotate, float* __restrict__ dst) {
+                long long map_ld, int OH, int OW, int flip, int rotate, float* __restrict__ dst, const __grid_constant__ CubicTab tab) {
     const long long total = (long long)N * OH * OW;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -46,8 +48,8 @@ k_remap_bicubic(const void* __restrict__ src, int N, int H, int W, const float* 
                              : (const void*)(reinterpret_cast<const float*>(src) + n * (long long)H * W);
         const int sx = __float2int_rn(__fmul_rn(mapx[i * map_ld + j], 32.f));   // cvRound(x * INTER_TAB_SIZE)
         const int sy = __float2int_rn(__fmul_rn(mapy[i * map_ld + j], 32.f));
-        const float* wx = c_cubic + (sx & 31) * 4;
-        const float* wy = c_cubic + (sy & 31) * 4;
+        const float* wx = tab.v + (sx & 31) * 4;
+        const float* wy = tab.v + (sy & 31) * 4;
         const int ix = min(max(sx >> 5, -32768), 32767) - 1;                 // saturate_cast<short>, then the 4x4 window starts one left/up
         const int iy = min(max(sy >> 5, -32768), 32767) - 1;
         float sum;
@@ -111,20 +113,14 @@ extern "C" int evfly_remap_bicubic_f32(const void* d_src, int src_is_u8, int N, 
                                        int64_t map_ld, int OH, int OW, int flip, int rotate, float* d_dst, void* stream) {
     EVFLY_REQUIRE(d_src && d_mapx && d_mapy && d_dst && N >= 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && map_ld >= OW, "remap_bicubic_f32: bad argument");
     if (N == 0) return EVFLY_OK;
-    static bool table_ready = false;
-    if (!table_ready) {
-        float tab[128];
-        cubic_table_host(tab);
-        EVFLY_CUDA(cudaMemcpyToSymbol(c_cubic, tab, sizeof(tab)));
-        table_ready = true;
-    }
+    static const CubicTab tab = [] { CubicTab t; cubic_table_host(t.v); return t; }();     // host-side, thread-safe (C++11 static init)
     const long long total = (long long)N * OH * OW;
     const int grid = stream_grid(total, 256, 16);
     cudaStream_t st = (cudaStream_t)stream;
     if (src_is_u8)
-        k_remap_bicubic<true><<<grid, 256, 0, st>>>(d_src, N, H, W, d_mapx, d_mapy, map_ld, OH, OW, flip, rotate, d_dst);
+        k_remap_bicubic<true><<<grid, 256, 0, st>>>(d_src, N, H, W, d_mapx, d_mapy, map_ld, OH, OW, flip, rotate, d_dst, tab);
     else
-        k_remap_bicubic<false><<<grid, 256, 0, st>>>(d_src, N, H, W, d_mapx, d_mapy, map_ld, OH, OW, flip, rotate, d_dst);
+        k_remap_bicubic<false><<<grid, 256, 0, st>>>(d_src, N, H, W, d_mapx, d_mapy, map_ld, OH, OW, flip, rotate, d_dst, tab);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }

@@ -445,17 +445,38 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
     return EVFLY_OK;
 }
 
+// cooperative = the persistent scan (n_steps > 1), whose CTAs meet at a grid-wide barrier between steps: launched with
+// cudaLaunchCooperativeKernel on a grid sized from the CURRENT device (SM count x occupancy), so every CTA is
+// guaranteed to be co-resident whatever the device / MIG slice / MPS limit and whatever else runs next to it
+// (a plain <<<>>> launch of min(tiles, 148) CTAs spins forever when some of them cannot become resident).
+// Returns EVFLY_ERR_UNSUPPORTED when the device cannot hold one CTA per launch: the caller then enqueues the steps one by one.
 template <int TN, int KC>
-static int launch_tc_maps(const CUtensorMap& map_a, const CUtensorMap& map_b, const TcArgs& p, cudaStream_t st) {
+static int launch_tc_maps(const CUtensorMap& map_a, const CUtensorMap& map_b, const TcArgs& p, cudaStream_t st, bool cooperative = false) {
     using Cfg = TcCfg<TN, KC>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv_bf16<TN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    EVFLY_SMEM_ATTR(Cfg::SMEM_BYTES, k_tc_conv_bf16<TN, KC>);
     const long long tiles = ceil_div(p.M_rows, Cfg::BM) * ceil_div(p.n_rows, TN);
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    k_tc_conv_bf16<TN, KC><<<grid, 384, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
+    if (!cooperative) {
+        const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+        k_tc_conv_bf16<TN, KC><<<grid, 384, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
+        EVFLY_LAUNCHED();
+        return EVFLY_OK;
+    }
+    int per_sm = 0;
+    EVFLY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_conv_bf16<TN, KC>, 384, Cfg::SMEM_BYTES));
+    const long long resident = (long long)(per_sm > 0 ? 1 : 0) * device_sm_count();       // one CTA per SM by design (TMEM, 1 CTA/SM smem)
+    if (resident < 1) {
+        set_error("convlstm scan: the persistent kernel cannot be made resident on this device");
+        return EVFLY_ERR_UNSUPPORTED;
+    }
+    const int grid = (int)(tiles < resident ? tiles : resident);
+    void* args[] = {(void*)&map_a, (void*)&map_b, (void*)&p};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tc_conv_bf16<TN, KC>, dim3(grid), dim3(384), args, Cfg::SMEM_BYTES, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        set_error("convlstm scan: cooperative launch of %d CTAs refused (%s)", grid, cudaGetErrorString(e));
+        return EVFLY_ERR_UNSUPPORTED;
+    }
+    EVFLY_CUDA(e);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }
@@ -566,22 +587,24 @@ extern "C" int evfly_convlstm_scan_bf16(void* d_h_all, const void* d_wh, const f
     __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(d_h_all);
     cudaStream_t st = (cudaStream_t)stream;
     p.n_steps = 1;
-    if (d_sync) {
-        // persistent: ONE launch walks all T steps; CTAs meet at a grid-wide barrier between steps. The grid is
-        // at most 148 CTAs of 1 CTA/SM, so all of them are co-resident and the spin-wait cannot deadlock.
+    if (d_sync && T > 1) {
+        // persistent: ONE cooperative launch walks all T steps; CTAs meet at a grid-wide barrier between steps
         EVFLY_CUDA(cudaMemsetAsync(d_sync, 0, 8, st));
-        p.n_steps = T;
-        p.a_row0 = 0;
-        p.a_row_step = P;
-        p.res = d_gx;
-        p.res_step = (long long)P * 4 * Ch;
-        p.lstm_h = h + (long long)P * Ch;
-        p.lstm_h_step = (long long)P * Ch;
-        p.sync_counter = reinterpret_cast<unsigned int*>(d_sync);
-        return tn == 32 ? launch_tc_maps<32, KC>(map_a, map_b, p, st)
-             : tn == 64 ? launch_tc_maps<64, KC>(map_a, map_b, p, st)
-             : tn == 128 ? launch_tc_maps<128, KC>(map_a, map_b, p, st)
-                         : launch_tc_maps<256, KC>(map_a, map_b, p, st);
+        TcArgs q = p;
+        q.n_steps = T;
+        q.a_row0 = 0;
+        q.a_row_step = P;
+        q.res = d_gx;
+        q.res_step = (long long)P * 4 * Ch;
+        q.lstm_h = h + (long long)P * Ch;
+        q.lstm_h_step = (long long)P * Ch;
+        q.sync_counter = reinterpret_cast<unsigned int*>(d_sync);
+        rc = tn == 32 ? launch_tc_maps<32, KC>(map_a, map_b, q, st, true)
+           : tn == 64 ? launch_tc_maps<64, KC>(map_a, map_b, q, st, true)
+           : tn == 128 ? launch_tc_maps<128, KC>(map_a, map_b, q, st, true)
+                       : launch_tc_maps<256, KC>(map_a, map_b, q, st, true);
+        if (rc != EVFLY_ERR_UNSUPPORTED) return rc;
+        // co-residency cannot be guaranteed here: fall through to one launch per step (same arithmetic, bit-identical)
     }
     for (int t = 0; t < T; ++t) {
         p.a_row0 = (long long)t * P;

@@ -452,11 +452,7 @@ static int launch_halo(const void* x, const void* w, const HaloArgs& p, cudaStre
     if (rc) return rc;
     rc = make_map_w(&mw, w, COUT, CIN);
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv3x3_halo<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
-    }
+    EVFLY_SMEM_ATTR(Cfg::SMEM_BYTES, k_tc_conv3x3_halo<CIN, COUT>);
     const long long tiles = (long long)p.tiles_x * p.tiles_y * p.N;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     k_tc_conv3x3_halo<CIN, COUT><<<grid, 384, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
@@ -472,11 +468,7 @@ static int launch_halo_ws(const void* x, const void* w, const HaloArgs& p, cudaS
     if (rc) return rc;
     rc = make_map_w(&mw, w, COUT, 128, 64);
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_tc_conv3x3_halo_ws<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
-    }
+    EVFLY_SMEM_ATTR(Cfg::SMEM_BYTES, k_tc_conv3x3_halo_ws<COUT>);
     const long long tiles = (long long)p.tiles_x * p.tiles_y * p.N;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     k_tc_conv3x3_halo_ws<COUT><<<grid, 384, Cfg::SMEM_BYTES, st>>>(mx, mw, p);

@@ -159,11 +159,7 @@ template <int NBLK, int COUT, bool F32_IN>
 static int launch_pe(const void* x, const float* w, const float* bias, const float* gamma, const float* beta, void* out, long long tokens, int H,
                      int W, int Cin, int k, int s, int p, int OH, int OW, float eps, cudaStream_t st) {
     constexpr int smem = NBLK * 16384 + NBLK * COUT * 128 + 1024;
-    static bool attr = false;
-    if (!attr) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_patch_embed_tc<NBLK, COUT, F32_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    EVFLY_SMEM_ATTR(smem, k_patch_embed_tc<NBLK, COUT, F32_IN>);
     const long long tiles = (tokens + 127) / 128;
     const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 8);
     const long long wave = (long long)kNumSMs * per_sm;

@@ -601,11 +601,7 @@ extern "C" int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, 
     EVFLY_REQUIRE(d_gx && d_whh_pairs && d_hs && T >= 0 && H > 0 && H % 2 == 0 && 4 * H <= 1024 && n_seq > 0, "lstm_seq_smemw: bad argument (H even, 4H <= 1024)");
     const size_t smem = (size_t)(H / 2) * 4 * H * 4 + (size_t)6 * H * 4;
     EVFLY_REQUIRE(smem <= 220 * 1024, "lstm_seq_smemw: W_hh does not fit shared memory (H=%d)", H);
-    static bool attr = false;
-    if (!attr) {
-        EVFLY_CUDA(cudaFuncSetAttribute(k_lstm_seq_smemw, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr = true;
-    }
+    EVFLY_SMEM_ATTR(220 * 1024, k_lstm_seq_smemw);
     const int threads = ((4 * H + 31) / 32) * 32;
     k_lstm_seq_smemw<<<n_seq, threads, smem, (cudaStream_t)stream>>>(d_gx, reinterpret_cast<const __nv_bfloat162*>(d_whh_pairs), d_h0, d_c0,
                                                                      d_hs, d_hT, d_cT, T, H, n_seq);

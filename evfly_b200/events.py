@@ -16,6 +16,11 @@ EVENT_DTYPE = np.dtype([
 ])
 assert EVENT_DTYPE.itemsize == 16
 
+# 8-byte wire record (include/evfly_b200.h evfly_event8): offset from the window's first edge instead of the
+# absolute time; x = 0xffff marks a skipped record
+EVENT8_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("dt_pol", "<u4")])
+assert EVENT8_DTYPE.itemsize == 8
+
 NS = 1_000_000_000
 
 
@@ -41,6 +46,66 @@ def make_records(x, y, t_ns, p) -> np.ndarray:
 
 def records_time_ns(rec: np.ndarray) -> np.ndarray:
     return rec["ts_sec"].astype(np.int64) * NS + rec["ts_nsec"].astype(np.int64)
+
+
+def pack_ev8_host(records: np.ndarray, edges_ns: np.ndarray):
+    """Host-side packer of the wire format (numpy): EVENT_DTYPE records of ONE time-sorted stream + window edges
+    int64 [T+1] -> (EVENT8_DTYPE records [n], win_offsets int64 [T+1]). Same result as L1.pack_ev8 on the device."""
+    t = records_time_ns(records)
+    edges_ns = np.asarray(edges_ns, dtype=np.int64)
+    offsets = np.searchsorted(t, edges_ns, side="left").astype(np.int64)
+    w = np.clip(np.searchsorted(offsets, np.arange(records.shape[0]), side="right") - 1, 0, len(edges_ns) - 2)
+    dt = t - edges_ns[w]
+    out = np.zeros(records.shape[0], dtype=EVENT8_DTYPE)
+    idx = np.arange(records.shape[0])
+    ok = (idx >= offsets[0]) & (idx < offsets[-1]) & (records["polarity"] < 2) & (dt >= 0) & (dt < (1 << 31)) & (t < edges_ns[w + 1])
+    out["x"] = np.where(ok, records["x"], 0xFFFF)
+    out["y"] = np.where(ok, records["y"], 0xFFFF)
+    out["dt_pol"] = np.where(ok, (dt.astype(np.uint64) << np.uint64(1)) | records["polarity"].astype(np.uint64), 0).astype(np.uint32)
+    return out, offsets
+
+
+class WireBatch:
+    """A batch of n_traj trajectories of T windows each in the 8-byte wire format, ready for
+    L1.accumulate_windows_ev8 / PerceptionPipeline: records of all trajectories laid end to end (uint8 [n,8]; a
+    pinned HOST tensor for the feeder, a device tensor for the pipeline) plus the small per-window tables
+    (device int64 / int32): event index range, time range, and the output slot t*n_traj + s (time-major frames:
+    the model advances the trajectories together)."""
+
+    def __init__(self, records, win_offsets, win_t0, win_t1, out_slot, n_traj, T):
+        self.records, self.win_offsets, self.win_t0, self.win_t1, self.out_slot = records, win_offsets, win_t0, win_t1, out_slot
+        self.n_traj, self.T = int(n_traj), int(T)
+
+    @property
+    def n_windows(self):
+        return self.n_traj * self.T
+
+    @staticmethod
+    def from_streams(streams, device, pin=True):
+        """streams: list of (EVENT_DTYPE records, edges int64 [T+1]) of equal T (host numpy). Packs on the host."""
+        T = len(streams[0][1]) - 1
+        assert all(len(e) - 1 == T for _, e in streams), "trajectories must have the same number of windows"
+        n = len(streams)
+        recs, offs, t0, t1, base = [], [], [], [], 0
+        for r, e in streams:
+            r8, o = pack_ev8_host(r, e)
+            recs.append(r8)
+            # window (s,t) = [base + o[t], next start): records of a trajectory that lie outside its windows were made
+            # skip records by the packer, so a range may harmlessly include them
+            offs.append(o[:-1] + base)
+            t0.append(np.asarray(e[:-1], np.int64)); t1.append(np.asarray(e[1:], np.int64))
+            base += r8.shape[0]
+        offs.append(np.array([base], dtype=np.int64))
+        host = torch.from_numpy(np.concatenate(recs).view(np.uint8).reshape(-1, 8))
+        if pin:
+            host = host.pin_memory()
+        slot = (np.arange(T, dtype=np.int32)[None, :] * n + np.arange(n, dtype=np.int32)[:, None]).reshape(-1)
+        dev = torch.device(device)
+        return WireBatch(host, torch.from_numpy(np.concatenate(offs)).to(dev), torch.from_numpy(np.concatenate(t0)).to(dev),
+                         torch.from_numpy(np.concatenate(t1)).to(dev), torch.from_numpy(slot).to(dev), n, T)
+
+    def on_device(self, device_records):
+        return WireBatch(device_records, self.win_offsets, self.win_t0, self.win_t1, self.out_slot, self.n_traj, self.T)
 
 
 def to_device(records, device=None, pinned: torch.Tensor | None = None) -> torch.Tensor:
@@ -182,10 +247,57 @@ class L1:
                    "evfly_voxelize_window")
         return counts, voxel
 
+    _sorted_ws: dict = {}
+
+    @staticmethod
+    def sorted_workspace(n, n_windows, H, W, B, device) -> torch.Tensor:
+        """Scratch of the shared-memory-tile path, cached per (device, stream) and grown on demand."""
+        need = _lib.load().evfly_accumulate_sorted_workspace_bytes(int(n), int(n_windows), H, W, 0 if B is None else B)
+        if need <= 0:
+            raise _lib.EvflyError(f"accumulate (tiled): unsupported shape H={H} W={W} B={B}")
+        key = (torch.device(device), torch.cuda.current_stream().cuda_stream)
+        ws = L1._sorted_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty((int(need * 1.25) + 4096,), dtype=torch.uint8, device=device)
+            L1._sorted_ws[key] = ws
+        return ws
+
+    @staticmethod
+    def pack_ev8(records, edges_ns: torch.Tensor):
+        """Device packer: canonical records [n,16] of one time-sorted stream -> (wire records uint8 [n,8], win_offsets int64 [T+1])."""
+        lib = _lib.load()
+        n, T = records.shape[0], edges_ns.shape[0] - 1
+        out = torch.empty((n, 8), dtype=torch.uint8, device=records.device)
+        offs = torch.empty((T + 1,), dtype=torch.int64, device=records.device)
+        _lib.check(lib.evfly_pack_events_ev8(_lib.ptr(records), n, _lib.ptr(edges_ns), T, _lib.ptr(out), _lib.ptr(offs), _lib.stream_ptr()),
+                   "evfly_pack_events_ev8")
+        return out, offs
+
+    @staticmethod
+    def accumulate_windows_ev8(records8, win_offsets, win_t0, win_t1, H, W, B=None, *, out_slot=None, n_slots=None, counts=None, voxel=None):
+        """Wire records uint8 [n,8] (any number of streams end to end) + per-window tables on the device ->
+        (counts int32 [n_slots,2,H,W], voxel fp32 [n_slots,B,H,W] | None); window w lands in slot out_slot[w] (default w)."""
+        lib = _lib.load()
+        dev = records8.device
+        nw = win_t0.shape[0]
+        n_slots = nw if n_slots is None else n_slots
+        if counts is None:
+            counts = torch.empty((n_slots, 2, H, W), dtype=torch.int32, device=dev)
+        if B is not None and voxel is None:
+            voxel = torch.empty((n_slots, B, H, W), dtype=torch.float32, device=dev)
+        ws = L1.sorted_workspace(records8.shape[0], nw, H, W, B, dev)
+        _lib.check(lib.evfly_accumulate_windows_ev8(_lib.ptr(records8), records8.shape[0], _lib.ptr(win_offsets), _lib.ptr(win_t0), _lib.ptr(win_t1),
+                                                    _lib.ptr(out_slot), nw, H, W, 0 if B is None else B, _lib.ptr(counts), _lib.ptr(voxel),
+                                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "evfly_accumulate_windows_ev8")
+        return counts, voxel
+
     @staticmethod
     def accumulate_windows(records, edges_ns: torch.Tensor, H, W, B=None, *, sorted_by_time=True,
-                           counts=None, voxel=None):
-        """edges_ns int64 CUDA [T+1]. Returns (counts int32 [T,2,H,W], voxel fp32 [T,B,H,W]|None)."""
+                           counts=None, voxel=None, algo="auto", slot_stride=1, slot_offset=0):
+        """edges_ns int64 CUDA [T+1]. Returns (counts int32 [T,2,H,W], voxel fp32 [T,B,H,W]|None).
+        algo: 'tiles' = shared-memory histogram tiles (time-sorted streams; window w goes to frame slot
+        w*slot_stride + slot_offset of the given buffers), 'scatter' = L2 reductions (any order), 'auto' = tiles
+        for sorted streams."""
         lib = _lib.load()
         dev = records.device
         T = edges_ns.shape[0] - 1
@@ -193,6 +305,18 @@ class L1:
             counts = torch.empty((T, 2, H, W), dtype=torch.int32, device=dev)
         if B is not None and voxel is None:
             voxel = torch.empty((T, B, H, W), dtype=torch.float32, device=dev)
+        if algo == "auto":
+            algo = "tiles" if sorted_by_time else "scatter"
+        if algo == "tiles":
+            if not sorted_by_time:
+                raise _lib.EvflyError("accumulate_windows(algo='tiles') needs a time-sorted stream")
+            ws = L1.sorted_workspace(records.shape[0], T, H, W, B, dev)
+            _lib.check(lib.evfly_accumulate_windows_sorted(_lib.ptr(records), records.shape[0], _lib.ptr(edges_ns), T, H, W, 0 if B is None else B,
+                                                           _lib.ptr(counts), _lib.ptr(voxel), int(slot_stride), int(slot_offset), _lib.ptr(ws),
+                                                           ws.numel(), _lib.stream_ptr()), "evfly_accumulate_windows_sorted")
+            return counts, voxel
+        if slot_stride != 1 or slot_offset != 0:
+            raise _lib.EvflyError("accumulate_windows(algo='scatter') writes consecutive frames only")
         rng = torch.empty((T + 1,), dtype=torch.int64, device=dev)
         _lib.check(lib.evfly_accumulate_windows(_lib.ptr(records), records.shape[0], _lib.ptr(edges_ns),
                                                 T, H, W, 0 if B is None else B, _lib.ptr(counts),

@@ -72,32 +72,59 @@ class PerceptionPipeline:
     def forward(self, frames, carry_state=True):
         """frames [T,1,h,w] = one sequence of T consecutive windows. Returns (vel [T,3], depth)."""
         T = frames.shape[0]
-        desvel = torch.full((T, 1), self.desvel, dtype=torch.float32, device=self.dev)
+        desvel = self._desvel(T)
         vel, (depth, _, ((hu, _), hv)) = self.model([frames, desvel, [self.state_unet, None], self.state_vit])
         if carry_state:
             self.state_unet, self.state_vit = hu, hv
         return vel, depth
 
     def frames_from_trajectories(self, records_list, edges_list, want_voxel=True, ready=None):
-        """L1 + L2 for n trajectories of equal length T: each trajectory is accumulated from its own event stream into
-        its slice of one [n,T,...] buffer, then ONE decode(+rectify)+crop and ONE quantile launch cover all n*T frames
-        (the per-frame work is independent). ready: optional CUDA events, one per trajectory, that the current stream
-        waits on before touching that trajectory's records (its host-to-device copy). Returns (frames [T*n,1,h,w] in
-        time-major order t*n + s, counts [n,T,2,H,W], voxel [n,T,B,H,W] | None)."""
-        lib = _lib.load()
+        """L1 + L2 for n trajectories of equal length T: each trajectory is accumulated from its own event stream
+        straight into its TIME-MAJOR frame slots t*n + s of one buffer (the model advances the trajectories
+        together), then ONE decode(+rectify)+crop+quantile launch covers all n*T frames. ready: optional CUDA
+        events, one per trajectory, that the current stream waits on before touching that trajectory's records
+        (its host-to-device copy). Returns (frames [T*n,1,h,w] time-major, counts view [n,T,2,H,W],
+        voxel view [n,T,B,H,W] | None)."""
         n = len(records_list)
         T = edges_list[0].shape[0] - 1
         assert all(e.shape[0] - 1 == T for e in edges_list), "trajectories must have the same number of windows"
-        counts = torch.empty((n, T, 2, self.H, self.W), dtype=torch.int32, device=self.dev)
-        voxel = torch.empty((n, T, self.B, self.H, self.W), dtype=torch.float32, device=self.dev) if want_voxel else None
+        counts = torch.empty((T * n, 2, self.H, self.W), dtype=torch.int32, device=self.dev)
+        voxel = torch.empty((T * n, self.B, self.H, self.W), dtype=torch.float32, device=self.dev) if want_voxel else None
         for s, (rec, edges) in enumerate(zip(records_list, edges_list)):
             if ready is not None:
                 torch.cuda.current_stream().wait_event(ready[s])
-            L1.accumulate_windows(rec, edges, self.H, self.W, self.B if want_voxel else None, counts=counts[s],
-                                  voxel=None if voxel is None else voxel[s])
-        frames = torch.empty((n, T, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
-        self._normalise(counts.view(n * T, 2, self.H, self.W), frames.view(n * T, 1, self.h, self.w))
-        return frames.transpose(0, 1).reshape(T * n, 1, self.h, self.w), counts, voxel
+            L1.accumulate_windows(rec, edges, self.H, self.W, self.B if want_voxel else None, counts=counts, voxel=voxel,
+                                  slot_stride=n, slot_offset=s)
+        frames = torch.empty((T * n, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
+        self._normalise(counts, frames)
+        return (frames, counts.view(T, n, 2, self.H, self.W).transpose(0, 1),
+                None if voxel is None else voxel.view(T, n, self.B, self.H, self.W).transpose(0, 1))
+
+    def frames_from_wire(self, wb, want_voxel=True):
+        """L1 + L2 for a WireBatch (8-byte wire records of n_traj trajectories x T windows, already on the device):
+        one accumulation call for all windows, frames in time-major slots. Same returns as frames_from_trajectories."""
+        n, T = wb.n_traj, wb.T
+        counts, voxel = L1.accumulate_windows_ev8(wb.records, wb.win_offsets, wb.win_t0, wb.win_t1, self.H, self.W,
+                                                  self.B if want_voxel else None, out_slot=wb.out_slot, n_slots=n * T)
+        frames = torch.empty((T * n, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
+        self._normalise(counts, frames)
+        return (frames, counts.view(T, n, 2, self.H, self.W).transpose(0, 1),
+                None if voxel is None else voxel.view(T, n, self.B, self.H, self.W).transpose(0, 1))
+
+    def _desvel(self, rows):
+        """[rows,1] tensor of the desired speed (cached: a torch.full per step is a launch that is not ours)."""
+        cache = self.__dict__.setdefault("_desvel_cache", {})
+        t = cache.get(rows)
+        if t is None:
+            t = cache[rows] = torch.full((rows, 1), self.desvel, dtype=torch.float32, device=self.dev)
+        return t
+
+    def run_wire(self, wb, want_voxel=True):
+        """Config 4 from the wire format: WireBatch on the device -> (vel [n_traj,T,3], depth [n_traj,T,1,h,w]); fresh state."""
+        n, T = wb.n_traj, wb.T
+        tm = self.frames_from_wire(wb, want_voxel)[0]
+        vel, (depth, _, _) = self.model.forward_trajectories([tm, self._desvel(T * n), [None, None], None], n)
+        return vel.view(T, n, 3).transpose(0, 1), depth.view(T, n, 1, self.h, self.w).transpose(0, 1)
 
     def run_trajectories(self, records_list, edges_list, want_voxel=True, ready=None):
         """Config 4: several independent trajectories of equal length T on one GPU. Each trajectory is accumulated
@@ -107,11 +134,15 @@ class PerceptionPipeline:
         n = len(records_list)
         tm = self.frames_from_trajectories(records_list, edges_list, want_voxel, ready=ready)[0]
         T = tm.shape[0] // n
-        desvel = torch.full((T * n, 1), self.desvel, dtype=torch.float32, device=self.dev)
+        desvel = self._desvel(T * n)
         vel, (depth, _, _) = self.model.forward_trajectories([tm, desvel, [None, None], None], n)
         return vel.view(T, n, 3).transpose(0, 1), depth.view(T, n, 1, self.h, self.w).transpose(0, 1)
 
     # ---- two-stage execution: L1+L2 of batch i+1 on a side stream while the model runs batch i -------------
+    def prefetch_wire(self, wb, want_voxel=True, ready=None, done_event=None):
+        """prefetch_trajectories() for a WireBatch on the device (ready: one CUDA event, its host-to-device copy)."""
+        return self.prefetch_trajectories(wb, None, want_voxel, ready=ready, done_event=done_event)
+
     def prefetch_trajectories(self, records_list, edges_list, want_voxel=True, ready=None, done_event=None):
         """Start L1 + L2 (accumulation, normalisation) of a batch of trajectories on the pipeline's side stream and
         return a handle for run_prefetched(). The scatter is bound by L2 reductions and the model by the tensor
@@ -126,12 +157,19 @@ class PerceptionPipeline:
         ps = self._prep_stream
         ps.wait_stream(main)                      # inputs (and the allocator's blocks) are ordered after what main has queued
         with torch.cuda.stream(ps):
-            tm, counts, voxel = self.frames_from_trajectories(records_list, edges_list, want_voxel, ready=ready)
+            if edges_list is None:                      # a WireBatch
+                if ready is not None:
+                    ps.wait_event(ready)
+                tm, counts, voxel = self.frames_from_wire(records_list, want_voxel)
+                n = records_list.n_traj
+            else:
+                tm, counts, voxel = self.frames_from_trajectories(records_list, edges_list, want_voxel, ready=ready)
+                n = len(records_list)
             if done_event is not None:
                 done_event.record(ps)
             ev = torch.cuda.Event()
             ev.record(ps)
-        return (tm, counts, voxel, ev, len(records_list))
+        return (tm, counts, voxel, ev, n)
 
     def run_prefetched(self, handle):
         """L3 for a batch prepared by prefetch_trajectories(). Returns (vel [n,T,3], depth [n,T,1,h,w])."""
@@ -142,7 +180,7 @@ class PerceptionPipeline:
             if t is not None:
                 t.record_stream(main)
         T = tm.shape[0] // n
-        desvel = torch.full((T * n, 1), self.desvel, dtype=torch.float32, device=self.dev)
+        desvel = self._desvel(T * n)
         vel, (depth, _, _) = self.model.forward_trajectories([tm, desvel, [None, None], None], n)
         return vel.view(T, n, 3).transpose(0, 1), depth.view(T, n, 1, self.h, self.w).transpose(0, 1)
 
@@ -160,19 +198,29 @@ class TrajectoryFeeder:
         feeder = TrajectoryFeeder(pipe, max_events, max_windows)
         for vel in feeder.run(batches):
             ...        # vel: pinned host tensor [n_traj, T, 3], valid until the next iteration
-    A batch is (records, edges) for one trajectory or ([records...], [edges...]) for several trajectories of equal
-    length that advance together (PerceptionPipeline.run_trajectories); records are pinned uint8 [n,16] host
-    tensors, edges int64 device tensors [T+1]."""
+    A batch is
+      * an evfly_b200.events.WireBatch whose records are a pinned HOST tensor (8-byte wire records of n_traj
+        trajectories, 8 bytes per event over PCIe), or
+      * (records, edges) for one trajectory / ([records...], [edges...]) for several trajectories of equal
+        length, records = pinned uint8 [n,16] host tensors of canonical records, edges int64 device tensors [T+1].
+    Multi-trajectory batches advance together (PerceptionPipeline.run_trajectories / run_wire)."""
 
-    def __init__(self, pipe: "PerceptionPipeline", max_events: int, max_windows: int):
+    def __init__(self, pipe: "PerceptionPipeline", max_events: int, max_windows: int, record_bytes: int = 16):
         dev = pipe.dev
         self.pipe = pipe
-        self.bufs = [torch.empty((max_events, 16), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.bufs = [torch.empty((max_events * record_bytes,), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [[] for _ in range(2)]                      # per slot: one event per trajectory, its H2D copy finished
         self.free = [torch.cuda.Event() for _ in range(2)]       # compute on slot finished
         self.h_vel = [torch.empty((max_windows, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_log = []                                        # (start event, end event, bytes) per staged batch
+
+    def h2d_gbs(self):
+        """Achieved host-to-device bandwidth of the staged copies (after a synchronize): (GB/s while copying, bytes)."""
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.h2d_log)
+        nbytes = sum(n for _, _, n in self.h2d_log)
+        return (nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0), nbytes
 
     @staticmethod
     def _as_lists(batch):
@@ -180,15 +228,40 @@ class TrajectoryFeeder:
         return (list(recs), list(edges)) if isinstance(recs, (list, tuple)) else ([recs], [edges])
 
     def _stage(self, slot, recs):
+        """recs: list of pinned host tensors [n_i, rb]; returns their device views inside the slot's buffer."""
+        views, off = [], 0
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.free[slot])
             while len(self.ready[slot]) < len(recs):
                 self.ready[slot].append(torch.cuda.Event())
-            off = 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.copy_stream)
             for s, r in enumerate(recs):
-                self.bufs[slot][off: off + r.shape[0]].copy_(r, non_blocking=True)
-                off += r.shape[0]
+                nb = r.numel()
+                v = self.bufs[slot][off: off + nb].view(r.shape)
+                v.copy_(r, non_blocking=True)
+                views.append(v)
+                off += (nb + 15) // 16 * 16
                 self.ready[slot][s].record(self.copy_stream)      # the pipeline starts on trajectory s while s+1 is still in flight
+            e1.record(self.copy_stream)
+            self.h2d_log.append((e0, e1, sum(r.numel() for r in recs)))
+        return views
+
+    def _start(self, slot, batch):
+        """H2D copy of `batch` into buffer `slot` and, for batches of several trajectories, its L1 + L2 on the
+        pipeline's side stream. Returns what _finish needs."""
+        from .events import WireBatch
+        if isinstance(batch, WireBatch):
+            (dev_recs,) = self._stage(slot, [batch.records])
+            h = self.pipe.prefetch_wire(batch.on_device(dev_recs), ready=self.ready[slot][0], done_event=self.free[slot])
+            return ("multi", h, batch.n_traj, batch.T)
+        recs, edges = self._as_lists(batch)
+        views = self._stage(slot, recs)
+        n, T = len(recs), edges[0].shape[0] - 1
+        if n > 1:
+            h = self.pipe.prefetch_trajectories(views, edges, ready=self.ready[slot][:n], done_event=self.free[slot])
+            return ("multi", h, n, T)
+        return ("single", (views[0], edges[0]), 1, T)
 
     def run(self, batches):
         it = iter(batches)
@@ -198,40 +271,23 @@ class TrajectoryFeeder:
         cur = next(it, None)
         if cur is None:
             return
-        self._stage(0, self._as_lists(cur)[0])
+        with torch.no_grad():
+            started = self._start(0, cur)
         slot = 0
         pending = None          # (slot, view) of the previous batch: its result is handed out one batch late, so the
                                 # host is always one batch ahead of the GPU and the launch queue never drains
-        handle = None           # L1+L2 of `cur`, started one iteration early on the pipeline's side stream
-
-        def views_of(slot_, recs_):
-            out_, off_ = [], 0
-            for r in recs_:
-                out_.append(self.bufs[slot_][off_: off_ + r.shape[0]])
-                off_ += r.shape[0]
-            return out_
-
         while cur is not None:
             nxt = next(it, None)
-            recs, edges = self._as_lists(cur)
-            n, T = len(recs), edges[0].shape[0] - 1
-            multi = n > 1
+            kind, h, n, T = started
             with torch.no_grad():
-                if multi and handle is None:
-                    handle = self.pipe.prefetch_trajectories(views_of(slot, recs), edges, ready=self.ready[slot][:n], done_event=self.free[slot])
-                nxt_handle = None
-                if nxt is not None:
-                    nrecs, nedges = self._as_lists(nxt)
-                    self._stage(slot ^ 1, nrecs)                          # H2D of batch i+1 ...
-                    if len(nrecs) > 1:                                     # ... and its L1+L2, both overlapping the model of batch i
-                        nxt_handle = self.pipe.prefetch_trajectories(views_of(slot ^ 1, nrecs), nedges, ready=self.ready[slot ^ 1][:len(nrecs)],
-                                                                     done_event=self.free[slot ^ 1])
+                # H2D of batch i+1 and (several trajectories) its L1+L2, both overlapping the model of batch i
+                nxt_started = self._start(slot ^ 1, nxt) if nxt is not None else None
                 self.pipe.reset()
-                if multi:
-                    vel = self.pipe.run_prefetched(handle)[0]
+                if kind == "multi":
+                    vel = self.pipe.run_prefetched(h)[0]
                 else:
                     main.wait_event(self.ready[slot][0])
-                    vel = self.pipe(views_of(slot, recs)[0], edges[0])[0].view(1, T, 3)
+                    vel = self.pipe(h[0], h[1])[0].view(1, T, 3)
                     self.free[slot].record(main)
                 out = self.h_vel[slot][: n * T].view(n, T, 3)
                 out.copy_(vel, non_blocking=True)
@@ -240,7 +296,7 @@ class TrajectoryFeeder:
                 self.done[pending[0]].synchronize()
                 yield pending[1]
             pending = (slot, out)
-            cur, slot, handle = nxt, slot ^ 1, nxt_handle
+            cur, slot, started = nxt, slot ^ 1, nxt_started
         if pending is not None:
             self.done[pending[0]].synchronize()
             yield pending[1]
@@ -264,6 +320,7 @@ class StreamingSession:
         self.records = skip.clone()
         self._n_prev = 0
         self.edges = torch.tensor([0, window_ns], dtype=torch.int64, device=dev)
+        self._edges_host = (0, int(window_ns))
         self.want_voxel = want_voxel
         m = pipe.model
         self.h_unet = torch.zeros((1, 512, 8, 13), dtype=torch.float32, device=dev)
@@ -300,7 +357,8 @@ class StreamingSession:
             t.zero_()
 
     def load_events(self, records: torch.Tensor, t0_ns: int = 0, window_ns: int | None = None):
-        """records uint8 [n,16] (device or pinned host); n <= capacity. Window = [t0, t0 + window)."""
+        """records uint8 [n,16] (device or pinned host); n <= capacity. Window = [t0, t0 + window); the edges are
+        rewritten whenever they differ from what the graph currently reads (also back to t0 = 0)."""
         n = records.shape[0]
         if n > self.cap:
             raise _lib.EvflyError(f"window of {n} events exceeds the session capacity {self.cap}")
@@ -308,9 +366,11 @@ class StreamingSession:
         if n < self._n_prev:
             self.records[n:self._n_prev].copy_(self._skip[n:self._n_prev])
         self._n_prev = n
-        if t0_ns != 0 or window_ns is not None:
-            w = int(self.edges[1] - self.edges[0]) if window_ns is None else window_ns
-            self.edges.copy_(torch.tensor([t0_ns, t0_ns + w], dtype=torch.int64), non_blocking=True)
+        w = self._edges_host[1] - self._edges_host[0] if window_ns is None else int(window_ns)
+        want = (int(t0_ns), int(t0_ns) + w)
+        if want != self._edges_host:
+            self._edges_host = want
+            self.edges.copy_(torch.tensor(want, dtype=torch.int64), non_blocking=True)
 
     def step(self, records: torch.Tensor | None = None, **kw) -> torch.Tensor:
         """One window -> velocity command [1,3] (device tensor, valid until the next step)."""

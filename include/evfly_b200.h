@@ -104,6 +104,45 @@ int evfly_pack_events_soa(const int64_t* d_x, const int64_t* d_y, const int64_t*
                           const int64_t* d_p, int64_t n, int H, int W, int pol_mode,
                           evfly_event* d_out, void* stream);
 
+/* ---- the 8-byte wire record ------------------------------------------------------------
+ * The canonical record with the absolute timestamp replaced by the offset from the first edge of the window
+ * the event has been assigned to (the host that slices a stream into windows -- utils/to_events.py:400-411,
+ * the 30 Hz timer of evfly_ros/src/node.cpp:42-59 -- knows that window). Half the bytes per event over PCIe.
+ * x == 0xffff marks a skipped record.                                                              */
+typedef struct evfly_event8 {
+    uint16_t x;
+    uint16_t y;
+    uint32_t dt_pol;      /* (t_ns - window_t0_ns) << 1 | polarity ; offsets up to 2^31 ns = 2.1 s */
+} evfly_event8;
+
+/* Canonical records of a time-sorted stream -> wire records, position by position, plus the event index range
+ * of every window: d_win_offsets int64 [T+1] (window w = records [off[w], off[w+1])). Records outside
+ * [edges[0], edges[T]), with polarity >= 2 or farther than 2^31 ns from their window's start become skips. */
+int evfly_pack_events_ev8(const evfly_event* d_events, int64_t n, const int64_t* d_edges_ns, int T,
+                          evfly_event8* d_out, int64_t* d_win_offsets, void* stream);
+
+/* Windows of a stream whose events are grouped by window, through shared-memory histogram tiles
+ * (evfly_b200/csrc/accumulate_tiled.cu): every chunk of 8192 events is counting-sorted by row band in shared
+ * memory, then one CTA per (band, window) accumulates the band's 2 + B planes in shared memory and writes them
+ * out once. No zero-fill, no global reduction; same results as evfly_accumulate_windows (counts bit-exact, voxel
+ * sums in a different order). Windows must be shorter than 2^32 ns (events farther from their window's start
+ * are dropped).
+ *   evfly_accumulate_windows_sorted : canonical records of ONE time-sorted stream, edges int64 [T+1]; window w
+ *       goes to frame slot w*slot_stride + slot_offset (1, 0: consecutive; n, s: trajectory s of a time-major batch)
+ *   evfly_accumulate_windows_ev8    : wire records of any number of streams laid end to end; window w is
+ *       records [d_win_offsets[w], d_win_offsets[w+1]) with time range [d_win_t0[w], d_win_t1[w]); its frame goes
+ *       to slot d_out_slot[w] of d_counts / d_voxel (NULL: slot w) -- e.g. time-major order for a batch of
+ *       trajectories (learner/evaluation_tools.py:62-66 evaluates them one by one).
+ * d_ws: evfly_accumulate_sorted_workspace_bytes(n, n_windows, H, W, B) bytes of scratch (any content).      */
+int64_t evfly_accumulate_sorted_workspace_bytes(int64_t n, int n_windows, int H, int W, int B);
+int evfly_accumulate_windows_sorted(const evfly_event* d_events, int64_t n, const int64_t* d_edges_ns, int T,
+                                    int H, int W, int B, int32_t* d_counts, float* d_voxel, int slot_stride,
+                                    int slot_offset, void* d_ws, int64_t ws_bytes, void* stream);
+int evfly_accumulate_windows_ev8(const evfly_event8* d_events, int64_t n, const int64_t* d_win_offsets,
+                                 const int64_t* d_win_t0, const int64_t* d_win_t1, const int32_t* d_out_slot,
+                                 int n_windows, int H, int W, int B, int32_t* d_counts, float* d_voxel, void* d_ws,
+                                 int64_t ws_bytes, void* stream);
+
 /* counts[pol][y][x] += #events, pol 0 = negative plane, 1 = positive plane; int32 [2,H,W].
  * Events with x >= W or y >= H (unsigned compare, node.cpp:31) or polarity >= 2 are ignored.
  * The caller zeroes d_counts (or keeps accumulating into it across calls, which is how the

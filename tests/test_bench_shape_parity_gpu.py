@@ -1,0 +1,171 @@
+"""GPU: the bf16 tensor-core path AT THE SHAPES bench.py TIMES, against the fp32 oracle (CPU).
+
+One tolerance, derived from BASELINE.json north_star ("depth maps and velocity commands match within rtol 1e-2
+for the bf16 path"), used for every tensor here:
+
+    |got - ref| <= RTOL * |ref| + ATOL_FRAC * max|ref|        RTOL = 1e-2, ATOL_FRAC = 1e-2
+
+i.e. numpy.allclose with rtol = 1e-2 and an absolute floor of 1 % of the tensor's own full scale (values that
+are sums with cancellation cannot carry a purely relative bound in any 8-bit-mantissa arithmetic). The tests
+report the ELEMENT-WISE PASS FRACTION under that bound plus the relative L2 error, assert both, and write the
+numbers to gpurun_out/parity_bench_shape.json (committed under profiles/ per round).
+
+Covered, because round 1 left them untested against the oracle ("weak" 1-2):
+  * forward_trajectories, n_traj = 4 x T = 100 (learner_models.py:544-546 ConvLSTM over T; vitfly_models.py:141-150
+    with N >= 16: _encode_tc + gemm_into_f32, k_lstm_seq_smemw with T >= 16),
+  * drift of the recurrent states -- ConvLSTM (h, c) and LSTM (h, c) -- after t = 1, 10, 50, 100 steps,
+  * one 256-step sequence (config 3),
+  * LSTMNetVIT alone at N = 32.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import evfly_b200
+from evfly_b200.pipeline import build_deployed_model
+from oracle import model_oracle as M
+from oracle.synth_ckpt import shapes_of, synth_state_dict, synthetic_depth, synthetic_frames
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL_FRAC = 1e-2, 1e-2
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT = os.path.join(ROOT, "gpurun_out", "parity_bench_shape.json")
+
+
+def parity(got, want):
+    g = got.detach().float().cpu().double().numpy()
+    w = want.detach().double().cpu().numpy()
+    assert g.shape == w.shape, (g.shape, w.shape)
+    err = np.abs(g - w)
+    full = float(np.abs(w).max())
+    ok = err <= RTOL * np.abs(w) + ATOL_FRAC * full
+    return {"pass_frac": float(ok.mean()), "rel_l2": float(np.linalg.norm(g - w) / max(np.linalg.norm(w), 1e-30)),
+            "max_err_over_fullscale": float(err.max() / max(full, 1e-30)), "fullscale": full, "n": int(w.size)}
+
+
+def record(section, data):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    try:
+        rep = json.load(open(REPORT))
+    except Exception:
+        rep = {"tolerance": f"|got-ref| <= {RTOL}*|ref| + {ATOL_FRAC}*max|ref|"}
+    rep[section] = data
+    json.dump(rep, open(REPORT, "w"), indent=1)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
+
+
+@pytest.fixture(scope="module")
+def deployed():
+    m = build_deployed_model("cpu")
+    sd = synth_state_dict(shapes_of(m), 31)
+    m.load_state_dict(sd)
+    return evfly_b200.set_precision(m.cuda().eval(), "bf16"), sd
+
+
+def oracle_chunks(sd, frames, marks):
+    """The oracle over one sequence, run in chunks that end at `marks` with the state carried (exact in fp32,
+    SURVEY F2), so that the recurrent states after t = marks[i] steps are available."""
+    T = frames.shape[0]
+    dv = torch.full((T, 1), 4.0)
+    hu, hv, t0 = None, None, 0
+    vels, deps, states = [], [], {}
+    for t1 in marks:
+        vel, (dep, _, ((hu, _), hv)) = M.orig_unet_w_vitlstm(sd, frames[t0:t1].clone(), dv[t0:t1], hu, hv, **M.DEPLOYED_UNET_CFG)
+        vels.append(vel); deps.append(dep)
+        states[t1] = (hu[0][0].clone(), hu[0][1].clone(), hv[0].clone(), hv[1].clone())
+        t0 = t1
+    return torch.cat(vels), torch.cat(deps), states
+
+
+def test_trajectories_bf16_at_bench_shape(cuda_lib, deployed):
+    """n_traj = 4, T = 100: the exact call bench.py times (forward_trajectories, time-major frames)."""
+    m, sd = deployed
+    n, T, marks = 4, 100, (1, 10, 50, 100)
+    frames = torch.stack([synthetic_frames(500 + s, T) for s in range(n)])            # [n,T,1,H,W]
+    ref = [oracle_chunks(sd, frames[s], marks) for s in range(n)]
+    rep = {"n_traj": n, "T": T}
+
+    def run(t_len):
+        tm = frames[:, :t_len].transpose(0, 1).reshape(t_len * n, 1, 260, 346).contiguous().cuda()
+        dv = torch.full((t_len * n, 1), 4.0, device="cuda")
+        vel, (dep, _, ((hu, _), hv)) = m.forward_trajectories([tm, dv, [None, None], None], n)
+        return vel.view(t_len, n, 3), dep.view(t_len, n, 1, 260, 346), hu[0], hv
+
+    vel, dep, hu, hv = run(T)
+    ovel = torch.stack([r[0] for r in ref], 1)                                          # [T,n,3]
+    odep = torch.stack([r[1] for r in ref], 1)
+    rep["depth"] = parity(dep, odep)
+    rep["velocity"] = parity(vel, ovel)
+    # per-step velocity error along the sequence (drift of what the caller consumes)
+    verr = (vel.cpu() - ovel).abs().amax(dim=(1, 2)) / ovel.abs().max()
+    rep["velocity_err_over_fullscale_at_t"] = {str(t): float(verr[t - 1]) for t in marks}
+    # recurrent-state drift after t steps: prefixes of the same trajectories from fresh state
+    drift = {}
+    for t in marks:
+        _, _, hu_t, hv_t = (vel, dep, hu, hv) if t == T else run(t)
+        o = [torch.stack([ref[s][2][t][k] for s in range(n)]) for k in range(4)]       # convlstm h, c [n,1,512,8,13]; lstm h, c [n,3,128]
+        drift[str(t)] = {"convlstm_h": parity(hu_t[0], o[0][:, 0]), "convlstm_c": parity(hu_t[1], o[1][:, 0]),
+                         "lstm_h": parity(hv_t[0], o[2].transpose(0, 1)), "lstm_c": parity(hv_t[1], o[3].transpose(0, 1))}
+    rep["state_drift_after_t_steps"] = drift
+    record("trajectories_4x100", rep)
+    print(json.dumps(rep))
+    assert rep["depth"]["pass_frac"] >= 0.99 and rep["depth"]["rel_l2"] <= 1e-2, rep["depth"]
+    assert rep["velocity"]["pass_frac"] >= 0.99 and rep["velocity"]["rel_l2"] <= 1e-2, rep["velocity"]
+    for t, d in drift.items():
+        for name, p in d.items():
+            assert p["rel_l2"] <= 2e-2 and p["pass_frac"] >= 0.97, (t, name, p)
+    # no growth: the error after 100 steps is not larger than a few times the error after 10
+    assert drift["100"]["convlstm_c"]["rel_l2"] <= 3 * max(drift["10"]["convlstm_c"]["rel_l2"], 2e-3)
+
+
+def test_sequence_256_bf16(cuda_lib, deployed):
+    """config 3: ONE 256-step sequence through forward() (the batch dimension is time)."""
+    m, sd = deployed
+    T = 256
+    frames = synthetic_frames(900, T)
+    dv = torch.full((T, 1), 4.0)
+    ovel, (odep, _, ((ohu, _), ohv)) = M.orig_unet_w_vitlstm(sd, frames.clone(), dv, None, None, **M.DEPLOYED_UNET_CFG)
+    vel, (dep, _, ((hu, _), hv)) = m([frames.clone().cuda(), dv.cuda(), [None, None], None])
+    rep = {"depth": parity(dep, odep), "velocity": parity(vel, ovel), "convlstm_h": parity(hu[0][0], ohu[0][0]),
+           "convlstm_c": parity(hu[0][1], ohu[0][1]), "lstm_h": parity(hv[0], ohv[0]), "lstm_c": parity(hv[1], ohv[1])}
+    record("sequence_256", rep)
+    print(json.dumps(rep))
+    assert rep["depth"]["pass_frac"] >= 0.99 and rep["depth"]["rel_l2"] <= 1e-2, rep["depth"]
+    assert rep["velocity"]["pass_frac"] >= 0.99 and rep["velocity"]["rel_l2"] <= 1e-2, rep["velocity"]
+    for k in ("convlstm_h", "convlstm_c", "lstm_h", "lstm_c"):
+        assert rep[k]["rel_l2"] <= 2e-2 and rep[k]["pass_frac"] >= 0.97, (k, rep[k])
+
+
+@pytest.mark.parametrize("N", [32, 100])
+def test_lstmnetvit_bf16_batch_path(cuda_lib, N):
+    """vitfly_models.py:141-150 with N >= 16: encoder tail + decoder Linear on the tensor cores (_encode_tc,
+    gemm_into_f32 with the NHWC-re-indexed decoder weight) and the shared-memory LSTM scan (T >= 16)."""
+    from tests.test_models_cpu import build
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_manifest.json")))
+    m = build("LSTMNetVIT")
+    sd = synth_state_dict(man["LSTMNetVIT"], 11)
+    m.load_state_dict(sd, strict=True)
+    m = evfly_b200.set_precision(m.cuda().eval().float(), "bf16")
+    depth = synthetic_depth(5, N)
+    dv = torch.full((N, 1), 4.0)
+    ovel, (oh, oc) = M.lstmnet_vit(sd, depth.clone(), dv, None)
+    vel, (h, c) = m([depth.clone().cuda(), dv.cuda(), None])
+    # the decoder Linear on its own: features in the reference's NCHW flatten order vs the re-indexed NHWC GEMM
+    feat_ref = M.linear_sn(sd, "decoder", M.vit_encoder_features(sd, depth))
+    pk = m.packed()
+    seq = torch.zeros((N, 517), dtype=torch.float32, device="cuda")
+    evfly_b200.tc.gemm_into_f32(m._encode_tc(depth.cuda(), pk["tail"]), pk["tail"]["dec"], m.decoder.bias, seq, 0)
+    rep = {"velocity": parity(vel, ovel), "lstm_h": parity(h, oh), "lstm_c": parity(c, oc), "decoder_features": parity(seq[:, :512], feat_ref)}
+    record(f"lstmnetvit_N{N}", rep)
+    print(json.dumps(rep))
+    for k, p in rep.items():
+        assert p["rel_l2"] <= 2e-2 and p["pass_frac"] >= 0.97, (k, p)

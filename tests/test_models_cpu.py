@@ -100,10 +100,17 @@ def test_no_cpu_fallback():
         m([torch.zeros(1, 1, 60, 90), torch.zeros(1, 1), None])
 
 
-def test_training_mode_with_grad_is_refused():
+def test_training_mode_is_refused_whatever_the_grad_mode():
+    """The kernels have eval-mode semantics (folded BatchNorm, no Dropout, no power iteration): train() mode would
+    diverge from the reference silently, so it raises with or without grad; eval() with grad enabled only warns."""
     m = VM.ViT()      # nn.Module default: training mode
     with pytest.raises(_lib.EvflyError):
         m._check_inference()
+    with torch.no_grad(), pytest.raises(_lib.EvflyError):
+        m._check_inference()
+    from evfly_b200._modbase import PackedModule
+    PackedModule._warned_grad = False
+    with pytest.warns(UserWarning):
+        m.eval()._check_inference()
     with torch.no_grad():
         m._check_inference()
-    m.eval()._check_inference()
