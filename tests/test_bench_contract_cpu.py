@@ -1,6 +1,6 @@
 """The driver-facing contract of bench.py that can be checked without a GPU: the reference arm
-(`--impl reference`: the oracle port of the reference's algorithm on the host cores) prints ONE JSON line with the
-agreed keys, under torchrun only rank 0 prints, and the GPU arm refuses to run without a GPU instead of falling back."""
+(`--impl reference`: the reference's own code from baseline/_ref on the host cores, else the oracle port of the same
+algorithm) prints ONE JSON line with the agreed keys, under torchrun only rank 0 prints, and the GPU arm refuses to run without a GPU instead of falling back."""
 import json
 import os
 import subprocess
@@ -26,7 +26,8 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["warmup"] >= 3 and d["steps"] == 1
     assert "workload" in d["config"] and "model" not in d["config"]
     cb, e2e = d["cpu_baseline"], d["e2e"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    want_kind = "reference" if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "learner", "learner_models.py")) else "port"
+    assert cb["kind"] == want_kind and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert e2e == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
