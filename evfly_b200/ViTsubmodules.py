@@ -103,8 +103,13 @@ class MixTransformerEncoderLayer(PackedModule):
     def _pack(self):
         c = self.patchMerge.cn1
         pk = {"patch_w": tc.pack_conv_kc(c.weight), "layers": []}
-        for attn, ffn in zip(self._attn, self._ffn):
+        for attn, ffn, ln in zip(self._attn, self._ffn, self._lNorm):
+            fused = None
+            if ffn.mlp1.out_features == 8 * ffn.mlp1.in_features and ffn.mlp1.in_features in (32, 64) and ffn.depthwise.weight.is_cuda:
+                fused = tc.pack_vit_ffn(ffn.mlp1.weight, ffn.mlp1.bias, ffn.depthwise.weight, ffn.depthwise.bias, ffn.mlp2.weight, ffn.mlp2.bias,
+                                        ln.weight, ln.bias)
             pk["layers"].append({
+                "ffn_fused": fused,
                 "red_w": tc.pack_conv_kc(attn.cn1.weight),
                 "kv": tc.pack_conv1x1_weight(attn.keyValueExtractor.weight), "q": tc.pack_conv1x1_weight(attn.query.weight),
                 "final": tc.pack_conv1x1_weight(attn.finalLayer.weight),
@@ -128,7 +133,11 @@ class MixTransformerEncoderLayer(PackedModule):
             q = tc.gemm_tokens(tok.view(-1, C), w["q"], attn.query.bias).view(B, N, C)
             att = tc.attention_small_bf16(q, kv, attn.heads)
             tok = tc.gemm_tokens(att.view(-1, C), w["final"], attn.finalLayer.bias, res_bf16=tok).view(B, N, C)      # x + attn(x)
-            # MixFFN: Linear -> grouped 3x3 + GELU -> Linear, residual in the last epilogue
+            # MixFFN + residual + LayerNorm: one launch, the 8C-wide activation never leaves the SM (csrc/vit_fused.cu)
+            if w["ffn_fused"] is not None and B >= tc.FUSED_FFN_MIN_BATCH and (H2, W2, C) in tc.FUSED_FFN_SHAPES:
+                tok = tc.vit_ffn(tok, w["ffn_fused"][0], w["ffn_fused"][1], B, H2, W2, ln.eps)
+                continue
+            # per-op path (small batches): Linear -> grouped 3x3 + GELU -> Linear, residual in the last epilogue
             y1 = tc.gemm_tokens(tok.view(-1, C), w["mlp1"], ffn.mlp1.bias)
             y2 = tc.dwconv3x3_gelu(y1.view(B, H2, W2, -1), ffn.depthwise.weight, ffn.depthwise.bias)
             tok = tc.gemm_tokens(y2.view(B * N, -1), w["mlp2"], ffn.mlp2.bias, res_bf16=tok).view(B, N, C)          # x + ffn(x)

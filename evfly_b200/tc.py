@@ -317,3 +317,59 @@ def gemm_into_f32(x2d, w_packed, bias, out_buf, out_c0):
     a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = K, Nn, 1, 0, 0, out_c0
     _call(a)
     return out_buf
+
+
+# ---- fused MixFFN block (csrc/vit_fused.cu) ---------------------------------------------------------
+FUSED_FFN_MIN_BATCH = 8      # below this one CTA per sample leaves the GPU empty: the per-op path is used (batch-1 streaming)
+FUSED_FFN_SHAPES = {(15, 23, 32), (8, 12, 64)}
+
+
+def _kmajor_swizzled(mat: torch.Tensor) -> torch.Tensor:
+    """[N, K] (K = 32 or 64) -> uint8 image [N*K*2] of a K-major UMMA operand whose base is 1024-byte aligned: row n holds
+    its K bf16 values in 16-byte chunks, chunk c stored at position c ^ ((n >> 1) & 3) (64-byte rows: SWIZZLE_64B) or
+    c ^ (n & 7) (128-byte rows: SWIZZLE_128B) -- what TMA would write and tcgen05.mma reads."""
+    N, K = mat.shape
+    assert K in (32, 64)
+    m = mat.to(BF16).contiguous().view(torch.int16).view(N, K // 8, 8)
+    n = torch.arange(N, device=mat.device)
+    c = torch.arange(K // 8, device=mat.device)
+    x = ((n >> 1) & 3) if K == 32 else (n & 7)
+    dst = (c[None, :] ^ x[:, None])[:, :, None].expand(-1, -1, 8)
+    out = torch.empty_like(m)
+    out.scatter_(1, dst, m)
+    return out.reshape(-1).view(torch.uint8)
+
+
+def pack_vit_ffn(mlp1_w, mlp1_b, dw_w, dw_b, mlp2_w, mlp2_b, ln_w, ln_b):
+    """Operand images of one MixFFN block for evfly_vit_ffn_bf16: per 32-channel slice of the expanded activation the
+    mlp1 rows [32, C], the nine conv taps as 32x32 block-diagonal matrices of the slice's four 8x8 groups
+    (depthwise.weight is [8C, 8, 3, 3] with groups = C: output channel co reads input channels 8*(co//8) .. +8), and the
+    mlp2 columns [C, 32]; all K-major and pre-swizzled. Returns (uint8 image, fp32 [8C + 8C + 3C] biases + LayerNorm)."""
+    Ce, Cc = mlp1_w.shape
+    dev = mlp1_w.device
+    parts = []
+    for j in range(Ce // 32):
+        sl = slice(32 * j, 32 * j + 32)
+        parts.append(_kmajor_swizzled(mlp1_w[sl]))
+        wj = dw_w[sl]                                        # [32, 8, 3, 3]
+        for tap in range(9):
+            bt = torch.zeros((32, 32), dtype=torch.float32, device=dev)
+            for gq in range(4):
+                bt[8 * gq:8 * gq + 8, 8 * gq:8 * gq + 8] = wj[8 * gq:8 * gq + 8, :, tap // 3, tap % 3]
+            parts.append(_kmajor_swizzled(bt))
+        parts.append(_kmajor_swizzled(mlp2_w[:, sl]))
+    img = torch.cat(parts).contiguous()
+    need = _lib.load().evfly_vit_ffn_image_bytes(Cc)
+    assert img.numel() == need, (img.numel(), need)
+    fb = torch.cat([mlp1_b, dw_b, mlp2_b, ln_w, ln_b]).to(torch.float32).contiguous()
+    return img, fb
+
+
+def vit_ffn(tok, img, fbias, B, H, W, eps):
+    """tok bf16 [B, H*W, C] -> LayerNorm(tok + MixFFN(tok)) bf16 [B, H*W, C] in one launch."""
+    Cc = tok.shape[-1]
+    assert tok.is_contiguous() and tok.dtype == BF16
+    out = torch.empty_like(tok)
+    _lib.check(_lib.load().evfly_vit_ffn_bf16(tok.data_ptr(), img.data_ptr(), _lib.ptr(fbias), out.data_ptr(), B, H, W, Cc, float(eps),
+                                              _lib.stream_ptr()), "evfly_vit_ffn_bf16")
+    return out

@@ -536,6 +536,16 @@ int evfly_tc_conv3x3_same_bf16(const void* d_x, const void* d_w, const float* d_
 int evfly_shuffle_upsample_cat_bf16(const void* d_t2, int H2, int W2, int C2, const void* d_t1, int H1, int W1,
                                     int C1, void* d_out, int64_t B, int ld, void* stream);
 
+/* One CTA per sample: a whole MixFFN block (learner/ViTsubmodules.py:85-120) + the residual add and the LayerNorm of
+ * MixTransformerEncoderLayer.forward (:143-146) on the tensor cores with the 8C-wide activation resident on chip:
+ *   out = LayerNorm(x + mlp2(GELU(groupedconv3x3(mlp1(x)))))
+ * d_tokens / d_out bf16 [B, H*W, C]; d_w_img = the pre-swizzled operand images of the block, evfly_vit_ffn_image_bytes(C)
+ * bytes (evfly_b200/tc.py::pack_vit_ffn); d_fbias fp32 = mlp1 bias [8C], conv bias [8C], mlp2 bias [C], LayerNorm
+ * gamma [C], beta [C]. Instantiated for the two stages of LSTMNetVIT / ViT: (H,W,C) = (15,23,32) and (8,12,64).        */
+int64_t evfly_vit_ffn_image_bytes(int C);
+int evfly_vit_ffn_bf16(const void* d_tokens, const void* d_w_img, const float* d_fbias, void* d_out, int B, int H, int W,
+                       int C, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
