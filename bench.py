@@ -329,7 +329,7 @@ class TrajectoryEvalWorkload:
         from evfly_b200 import tc
         torch = self.torch
         self._ev = getattr(self, "_ev", [])
-        hooks = ("_call", "_call_halo", "_call_halo_pool", "_call_scan")       # every launcher of the tcgen05 conv/GEMM kernels
+        hooks = ("_call", "_call_halo", "_call_halo_pool", "_call_scan", "_call_stem_e12")       # every launcher of the tcgen05 conv/GEMM kernels
         orig = {h: getattr(tc, h) for h in hooks}
 
         def timed(fn):

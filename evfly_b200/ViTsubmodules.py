@@ -108,8 +108,11 @@ class MixTransformerEncoderLayer(PackedModule):
             if ffn.mlp1.out_features == 8 * ffn.mlp1.in_features and ffn.mlp1.in_features in (32, 64) and ffn.depthwise.weight.is_cuda:
                 fused = tc.pack_vit_ffn(ffn.mlp1.weight, ffn.mlp1.bias, ffn.depthwise.weight, ffn.depthwise.bias, ffn.mlp2.weight, ffn.mlp2.bias,
                                         ln.weight, ln.bias)
+            attn_fused = None
+            if attn.query.in_features in (32, 64) and attn.query.in_features // attn.heads == 32 and attn.query.weight.is_cuda:
+                attn_fused = tc.pack_vit_attn(attn.query.weight, attn.query.bias, attn.finalLayer.weight, attn.finalLayer.bias)
             pk["layers"].append({
-                "ffn_fused": fused,
+                "ffn_fused": fused, "attn_fused": attn_fused,
                 "red_w": tc.pack_conv_kc(attn.cn1.weight),
                 "kv": tc.pack_conv1x1_weight(attn.keyValueExtractor.weight), "q": tc.pack_conv1x1_weight(attn.query.weight),
                 "final": tc.pack_conv1x1_weight(attn.finalLayer.weight),
@@ -130,9 +133,12 @@ class MixTransformerEncoderLayer(PackedModule):
             # spatial-reduction attention: k=s=r conv + LayerNorm fused, K/V and Q projections, few-key softmax
             red, h2, w2 = tc.patch_embed_ln(tok, False, w["red_w"], attn.cn1.bias, attn.ln1.weight, attn.ln1.bias, B, H2, W2, C, C, r, r, 0, attn.ln1.eps)
             kv = tc.gemm_tokens(red.view(-1, C), w["kv"], attn.keyValueExtractor.bias).view(B, h2 * w2, 2 * C)
-            q = tc.gemm_tokens(tok.view(-1, C), w["q"], attn.query.bias).view(B, N, C)
-            att = tc.attention_small_bf16(q, kv, attn.heads)
-            tok = tc.gemm_tokens(att.view(-1, C), w["final"], attn.finalLayer.bias, res_bf16=tok).view(B, N, C)      # x + attn(x)
+            if w["attn_fused"] is not None and tc.FUSED_ATTN and h2 * w2 <= 8:
+                tok = tc.vit_attn(tok, kv, w["attn_fused"][0], w["attn_fused"][1], attn.heads)                       # x + attn(x), one launch
+            else:
+                q = tc.gemm_tokens(tok.view(-1, C), w["q"], attn.query.bias).view(B, N, C)
+                att = tc.attention_small_bf16(q, kv, attn.heads)
+                tok = tc.gemm_tokens(att.view(-1, C), w["final"], attn.finalLayer.bias, res_bf16=tok).view(B, N, C)  # x + attn(x)
             # MixFFN + residual + LayerNorm: one launch, the 8C-wide activation never leaves the SM (csrc/vit_fused.cu)
             if w["ffn_fused"] is not None and B >= tc.FUSED_FFN_MIN_BATCH and (H2, W2, C) in tc.FUSED_FFN_SHAPES:
                 tok = tc.vit_ffn(tok, w["ffn_fused"][0], w["ffn_fused"][1], B, H2, W2, ln.eps)

@@ -404,6 +404,185 @@ k_tc_conv3x3_halo_ws(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Level 1 of the UNet with a BINARY input (form_BEV = 2, every shipped configuration: learner/configs/*.txt:39-47;
+// learner_models.py:489-491 turns the frame into a 0/1 mask): unet_e11 (1 -> 32, 3x3 valid, +bias, ReLU) has only 2^9
+// possible outputs per pixel, one per 3x3 pattern of mask bits. The stem therefore never runs as a convolution and its
+// output never exists in HBM: a tiny kernel turns the mask into one 9-bit pattern per e11 pixel, this kernel builds the
+// 512 x 32-channel table of e11 values once per CTA (bf16-rounded weights, fp32 sums, bias, ReLU, bf16 -- what the
+// tensor-core stem computes) and its producer warps assemble the 18x10 halo of every e12 tile by copying table rows
+// into the swizzled operand layout a TMA load of e11 would have produced. MMA issue and epilogue (+ fused MaxPool2d(2))
+// are those of k_tc_conv3x3_halo<32,32>. Against round 1 (stem kernel: 64 B written per pixel; e12: the same 64 B read
+// back) level 1 loses 128 of its 212 bytes of HBM traffic per pixel.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stem_patterns(const float* __restrict__ mask, uint16_t* __restrict__ pat, int N, int H, int W) {
+    const int EH = H - 2, EW = W - 2;
+    const long long total = (long long)N * EH * EW;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int ex = (int)(i % EW), ey = (int)((i / EW) % EH);
+        const long long n = i / ((long long)EW * EH);
+        const float* src = mask + (n * H + ey) * (long long)W + ex;
+        unsigned bits = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) bits |= (__ldg(src + (k / 3) * W + (k % 3)) != 0.f ? 1u : 0u) << k;
+        pat[i] = (uint16_t)bits;
+    }
+}
+
+struct StemE12Args {
+    const uint16_t* pat;      // [N, Hp-2, Wp-2] 3x3 mask patterns of the e11 pixels
+    const float* stem_w;      // unet_e11.weight [32][9]
+    const float* stem_b;      // [32]
+};
+
+constexpr int kStemProducers = 96;      // warps 0, 2, 3
+
+__global__ void __launch_bounds__(384, 1)
+k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const StemE12Args sa) {
+    using Cfg = HaloCfg<32, 32>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                                  // [9][32][32] swizzled per tap
+    uint8_t* s_halo = smem + Cfg::W_BYTES;                // [STAGES][180][32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_halo + Cfg::STAGES * Cfg::HALO_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::STAGES;
+    uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+    uint64_t* tempty_bar = tfull_bar + Cfg::NACC;
+    uint64_t* w_bar = tempty_bar + Cfg::NACC;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(w_bar + 2);
+    uint8_t* s_ostage = s_halo + Cfg::STAGES * Cfg::HALO_BYTES + 2048;
+    uint8_t* s_lut = s_ostage + Cfg::OUT_STAGE_BYTES;     // [512][32] bf16 = 64 B per pattern
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int total_tiles = tiles_per_img * p.N;
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&map_w);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < Cfg::NACC; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    // the e11 table: entry (pattern, channel pair)
+    for (int i = threadIdx.x; i < 512 * 16; i += 384) {
+        const int pt = i >> 4, c2 = (i & 15) * 2;
+        float a0 = sa.stem_b[c2], a1 = sa.stem_b[c2 + 1];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            if (pt & (1 << k)) {
+                a0 += __bfloat162float(__float2bfloat16_rn(sa.stem_w[c2 * 9 + k]));
+                a1 += __bfloat162float(__float2bfloat16_rn(sa.stem_w[(c2 + 1) * 9 + k]));
+            }
+        __nv_bfloat162 v = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+        reinterpret_cast<__nv_bfloat162*>(s_lut)[i] = v;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ================= halo producers: pattern -> table row -> swizzled operand row =================
+        const int pt_id = (warp == 0 ? 0 : warp - 1) * 32 + lane;            // 0..95
+        if (pt_id == 0) {
+            mbar_expect_tx(w_bar, Cfg::W_BYTES);
+            for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * Cfg::W_TAP_BYTES, &map_w, w_bar, t * 32, 0);
+        }
+        const int EH = p.Hp - 2, EW = p.Wp - 2;
+        // halo pixels of this thread: idx = pt_id and pt_id + 96 (180 per tile)
+        const int i0 = pt_id, i1 = pt_id + kStemProducers;
+        const int hy0 = i0 / 10, hx0 = i0 - hy0 * 10, hy1 = i1 / 10, hx1 = i1 - hy1 * 10;
+        auto fetch = [&](int tile, unsigned& q0, unsigned& q1) {
+            const int n = tile / tiles_per_img;
+            const int rem = tile - n * tiles_per_img;
+            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            const uint16_t* base = sa.pat + (long long)n * EH * EW;
+            const int y0 = ty * 16 + hy0, x0 = tx * 8 + hx0, y1 = ty * 16 + hy1, x1 = tx * 8 + hx1;
+            q0 = (y0 < EH && x0 < EW) ? (unsigned)__ldg(base + (long long)y0 * EW + x0) : 0u;
+            q1 = (i1 < Cfg::HALO_ROWS && y1 < EH && x1 < EW) ? (unsigned)__ldg(base + (long long)y1 * EW + x1) : 0u;
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        unsigned q0 = 0, q1 = 0;
+        if ((int)blockIdx.x < total_tiles) fetch(blockIdx.x, q0, q1);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            unsigned n0 = 0, n1 = 0;
+            if (tile + (int)gridDim.x < total_tiles) fetch(tile + gridDim.x, n0, n1);      // next tile's patterns: in flight during this copy
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* dst = s_halo + stage * Cfg::HALO_BYTES;
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q0 * 64);
+                const uint32_t sw = (uint32_t)(i0 >> 1) & 3u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + i0 * 64 + ((c ^ sw) << 4)) = src[c];
+            }
+            if (i1 < Cfg::HALO_ROWS) {
+                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q1 * 64);
+                const uint32_t sw = (uint32_t)(i1 >> 1) & 3u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + i1 * 64 + ((c ^ sw) << 4)) = src[c];
+            }
+            fence_proxy_async();                                                   // generic-proxy writes -> visible to tcgen05.mma
+            asm volatile("bar.sync 2, 96;" ::: "memory");                          // all producer threads have written and fenced
+            if (pt_id == 0) mbar_arrive(&full_bar[stage]);
+            q0 = n0;
+            q1 = n1;
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (as k_tc_conv3x3_halo) =================
+        constexpr uint32_t idesc = make_idesc_bf16(128, 32);
+        mbar_wait(w_bar, 0);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const uint64_t dw0 = make_smem_desc(smem_u32(s_w), Cfg::SBO_B, Cfg::LAYOUT);
+        const uint64_t dh0 = make_smem_desc(smem_u32(s_halo), Cfg::SBO_A, Cfg::LAYOUT);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
+            const uint64_t da0 = dh0 + (uint64_t)(stage * (Cfg::HALO_BYTES >> 4));
+            if (elect_one()) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint64_t da = da0 + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * Cfg::ROW_B + k * 32) >> 4);
+                        const uint64_t db = dw0 + (uint64_t)((tap * Cfg::W_TAP_BYTES + k * 32) >> 4);
+                        umma_bf16(tmem_d, da, db, idesc, (tap | k) != 0);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        halo_epilogue<32, Cfg::NACC, true>(p, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_ostage, total_tiles, tiles_per_img);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // input grid [N, Hp, Wp, C] as a 4-D tensor (C fastest), box [1, 18, 10, C]
 static int make_map_halo(CUtensorMap* map, const void* base, int N, int Hp, int Wp, int C, int box_c = 0) {
     PFN_encodeTiled enc = get_encode_fn();
@@ -527,4 +706,50 @@ extern "C" int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w,
 extern "C" int evfly_tc_conv3x3_same_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int H, int W, int Cin,
                                           int Cout, int relu, void* stream) {
     return halo_conv(d_x, d_w, d_bias, d_out, nullptr, N, H, W, H, W, Cin, Cout, relu, 0, 0, stream, 1);
+}
+
+extern "C" int evfly_stem_patterns(const float* d_mask, uint16_t* d_pat, int N, int H, int W, void* stream) {
+    EVFLY_REQUIRE(d_mask && d_pat && N >= 0 && H >= 3 && W >= 3, "stem_patterns: bad argument");
+    if (N == 0) return EVFLY_OK;
+    const long long total = (long long)N * (H - 2) * (W - 2);
+    k_stem_patterns<<<stream_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(d_mask, d_pat, N, H, W);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w, const float* d_bias,
+                                           void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2, int Wp2, void* stream) {
+    EVFLY_REQUIRE(d_pat && d_stem_w && d_stem_b && d_w && d_out && N > 0 && H >= 5 && W >= 5, "tc_stem_e12_pool_bf16: bad argument");
+    HaloArgs p;
+    p.bias = d_bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(d_out);
+    p.N = N;
+    p.Hp = H;
+    p.Wp = W;
+    p.pad = 0;
+    p.out_vh = H - 4;
+    p.out_vw = W - 4;
+    p.tiles_x = (p.out_vw + 7) / 8;
+    p.tiles_y = (p.out_vh + 15) / 16;
+    p.relu = relu;
+    p.pool_out = reinterpret_cast<__nv_bfloat16*>(d_pool);
+    p.Hp2 = Hp2;
+    p.Wp2 = Wp2;
+    EVFLY_REQUIRE(!d_pool || (Hp2 >= (H - 4) / 2 && Wp2 >= (W - 4) / 2), "tc_stem_e12_pool_bf16: pooled grid smaller than (H-4)/2 x (W-4)/2");
+    EVFLY_REQUIRE((long long)p.tiles_x * p.tiles_y * N < (1ll << 31), "tc_stem_e12_pool_bf16: too many tiles");
+    StemE12Args sa;
+    sa.pat = d_pat;
+    sa.stem_w = d_stem_w;
+    sa.stem_b = d_stem_b;
+    using Cfg = HaloCfg<32, 32>;
+    constexpr int smem = Cfg::SMEM_BYTES + 512 * 64;
+    CUtensorMap mw;
+    const int rc = make_map_w(&mw, d_w, 32, 32);
+    if (rc) return rc;
+    EVFLY_SMEM_ATTR(smem, k_tc_stem_e12);
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    k_tc_stem_e12<<<grid, 384, smem, (cudaStream_t)stream>>>(mw, p, sa);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
 }

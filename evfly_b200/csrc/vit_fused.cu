@@ -343,6 +343,207 @@ k_vit_ffn(const __nv_bfloat16* __restrict__ tokens, const uint8_t* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EfficientSelfAttention after the spatial reduction (learner/ViTsubmodules.py:74-83) + the residual of :144, one launch:
+//     out = x + finalLayer( softmax(Q K^T / sqrt(d)) V ),   Q = query(x)
+// K, V = keyValueExtractor(LayerNorm(cn1(x))) are 2..6 tokens per sample, computed by the launches in front
+// (kv bf16 [B, n_kv, 2C], layout [kv][head][d] like ViTsubmodules.py:74). Per tile of 128 tokens: Q on tcgen05 ->
+// TMEM -> every thread owns one token: few-key softmax in registers -> the attention row goes back to shared memory as
+// the A operand of the final projection -> tcgen05 -> + bias + residual -> bf16. Round 1 ran this as three launches
+// (two GEMMs and a CUDA-core attention kernel) with q and the attention output going through HBM/L2.
+template <int C, int HEADS>
+__global__ void __launch_bounds__(128)
+k_vit_attn(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ kv, const uint8_t* __restrict__ w_img,
+           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, long long rows, int N, int n_kv, int n_tiles) {
+    constexpr int ROWB = C * 2;
+    constexpr int DH = C / HEADS;
+    static_assert(DH == 32, "head dimension 32 (both stages of the reference's ViT)");
+    constexpr uint32_t LAYOUT = (C == 64) ? kLayoutSw128 : kLayoutSw64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_a = smem;                         // [128][ROWB]  x tile
+    uint8_t* s_p = s_a + 128 * ROWB;             // [128][ROWB]  attention rows
+    uint8_t* s_wq = s_p + 128 * ROWB;            // [C][ROWB]
+    uint8_t* s_wf = s_wq + C * ROWB;             // [C][ROWB]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_bq[C], s_bf[C];
+    const int t = threadIdx.x, warp = t >> 5;
+    if (warp == 0) tmem_alloc(&s_tmem, 2 * C);
+    if (t == 0) {
+        mbar_init(&s_bar, 1);
+        fence_barrier_init();
+    }
+    if (t < C) {
+        s_bq[t] = bias[t];
+        s_bf[t] = bias[C + t];
+    }
+    for (int i = t; i < 2 * C * ROWB / 16; i += 128) reinterpret_cast<uint4*>(s_wq)[i] = __ldg(reinterpret_cast<const uint4*>(w_img) + i);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const uint64_t da = make_smem_desc(smem_u32(s_a), 8 * ROWB, LAYOUT), dp = make_smem_desc(smem_u32(s_p), 8 * ROWB, LAYOUT);
+    const uint64_t dq = make_smem_desc(smem_u32(s_wq), 8 * ROWB, LAYOUT), df = make_smem_desc(smem_u32(s_wf), 8 * ROWB, LAYOUT);
+    constexpr uint32_t idesc = make_idesc_bf16(128, C);
+    const float scale = rsqrtf((float)DH);
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row = (long long)tile * 128 + t;
+        const bool live = row < rows;
+        {   // x tile -> swizzled A operand
+            const uint4* src = reinterpret_cast<const uint4*>(x + row * C);
+#pragma unroll
+            for (int c16 = 0; c16 < C / 8; ++c16)
+                *reinterpret_cast<uint4*>(s_a + swz<ROWB>(t, c16)) = live ? __ldg(src + c16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < C / 16; ++k) umma_bf16(tmem_base, da + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k != 0);
+                umma_commit(&s_bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- few-key attention of this thread's token
+        {
+            const long long b = live ? row / N : 0;
+            const __nv_bfloat16* kvb = kv + b * (long long)n_kv * 2 * C;
+#pragma unroll
+            for (int h = 0; h < HEADS; ++h) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + h * DH, r);
+                tmem_ld_wait();
+                float q[DH];
+#pragma unroll
+                for (int d = 0; d < DH; ++d) q[d] = __uint_as_float(r[d]) + s_bq[h * DH + d];
+                float sc[8];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    sc[j] = -INFINITY;
+                    if (j < n_kv) {
+                        const uint4* kp = reinterpret_cast<const uint4*>(kvb + (long long)j * 2 * C + h * DH);
+                        float dot = 0.f;
+#pragma unroll
+                        for (int c8 = 0; c8 < DH / 8; ++c8) {
+                            const uint4 kk = __ldg(kp + c8);
+                            const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&kk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(pk[e]);
+                                dot = fmaf(q[c8 * 8 + 2 * e], f.x, dot);
+                                dot = fmaf(q[c8 * 8 + 2 * e + 1], f.y, dot);
+                            }
+                        }
+                        sc[j] = dot * scale;
+                        mx = fmaxf(mx, sc[j]);
+                    }
+                }
+                float den = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    sc[j] = j < n_kv ? __expf(sc[j] - mx) : 0.f;
+                    den += sc[j];
+                }
+                const float inv = 1.f / den;
+                float att[DH];
+#pragma unroll
+                for (int d = 0; d < DH; ++d) att[d] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < n_kv) {
+                        const uint4* vp = reinterpret_cast<const uint4*>(kvb + (long long)j * 2 * C + C + h * DH);
+                        const float pj = sc[j] * inv;
+#pragma unroll
+                        for (int c8 = 0; c8 < DH / 8; ++c8) {
+                            const uint4 vv = __ldg(vp + c8);
+                            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(pv[e]);
+                                att[c8 * 8 + 2 * e] = fmaf(pj, f.x, att[c8 * 8 + 2 * e]);
+                                att[c8 * 8 + 2 * e + 1] = fmaf(pj, f.y, att[c8 * 8 + 2 * e + 1]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c8 = 0; c8 < DH / 8; ++c8)
+                    *reinterpret_cast<uint4*>(s_p + swz<ROWB>(t, h * (DH / 8) + c8)) =
+                        live ? make_uint4(pack_bf16x2(att[c8 * 8], att[c8 * 8 + 1]), pack_bf16x2(att[c8 * 8 + 2], att[c8 * 8 + 3]),
+                                          pack_bf16x2(att[c8 * 8 + 4], att[c8 * 8 + 5]), pack_bf16x2(att[c8 * 8 + 6], att[c8 * 8 + 7]))
+                             : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < C / 16; ++k) umma_bf16(tmem_base + C, dp + (uint64_t)(k * 2), df + (uint64_t)(k * 2), idesc, k != 0);
+                umma_commit(&s_bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- final projection epilogue: + bias + residual -> bf16
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + C + c0, r);
+            tmem_ld_wait();
+            if (live) {
+                const uint4* res = reinterpret_cast<const uint4*>(x + row * C + c0);
+                uint4* o = reinterpret_cast<uint4*>(out + row * C + c0);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const uint4 rr = __ldg(res + c8);
+                    const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&rr);
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(pr[e]);
+                        const int c = c0 + c8 * 8 + 2 * e;
+                        pk[e] = pack_bf16x2(__uint_as_float(r[c8 * 8 + 2 * e]) + s_bf[c] + f.x, __uint_as_float(r[c8 * 8 + 2 * e + 1]) + s_bf[c + 1] + f.y);
+                    }
+                    o[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * C);
+    }
+}
+
+template <int C, int HEADS>
+static int launch_attn(const void* x, const void* kv, const void* w_img, const float* bias, void* out, long long rows, int N, int n_kv, cudaStream_t st) {
+    constexpr int smem = 1024 + 2 * 128 * C * 2 + 2 * C * C * 2;
+    EVFLY_SMEM_ATTR(smem, k_vit_attn<C, HEADS>);
+    const long long tiles = (rows + 127) / 128;
+    const long long cap = (long long)kNumSMs * (C == 32 ? 6 : 3);
+    k_vit_attn<C, HEADS><<<(int)(tiles < cap ? tiles : cap), 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(kv),
+                                                                            reinterpret_cast<const uint8_t*>(w_img), bias, reinterpret_cast<__nv_bfloat16*>(out), rows,
+                                                                            N, n_kv, (int)tiles);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
 template <int C, int TH, int TW>
 static int launch_ffn(const void* tokens, const void* w_img, const float* fbias, void* out, int B, float eps, cudaStream_t st) {
     using Cfg = FfnCfg<C, TH, TW>;
@@ -374,5 +575,20 @@ extern "C" int evfly_vit_ffn_bf16(const void* d_tokens, const void* d_w_img, con
     if (C == 32 && H == 15 && W == 23) return launch_ffn<32, 15, 23>(d_tokens, d_w_img, d_fbias, d_out, B, eps, st);
     if (C == 64 && H == 8 && W == 12) return launch_ffn<64, 8, 12>(d_tokens, d_w_img, d_fbias, d_out, B, eps, st);
     set_error("vit_ffn_bf16: the fused MixFFN kernel is instantiated for the two stages of LSTMNetVIT / ViT (15x23x32 and 8x12x64), got %dx%dx%d", H, W, C);
+    return EVFLY_ERR_UNSUPPORTED;
+}
+
+extern "C" int evfly_vit_attn_bf16(const void* d_x, const void* d_kv, const void* d_w_img, const float* d_bias, void* d_out, int64_t B, int N, int C,
+                                   int heads, int n_kv, void* stream) {
+    EVFLY_REQUIRE(d_x && d_kv && d_w_img && d_bias && d_out && B >= 0 && N > 0 && n_kv >= 1 && n_kv <= 8, "vit_attn_bf16: bad argument (1 <= n_kv <= 8)");
+    EVFLY_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_kv) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w_img) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "vit_attn_bf16: operands must be 16-byte aligned");
+    if (B == 0) return EVFLY_OK;
+    const long long rows = (long long)B * N;
+    EVFLY_REQUIRE(rows < (1ll << 31) * 64, "vit_attn_bf16: too many tokens");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 32 && heads == 1) return launch_attn<32, 1>(d_x, d_kv, d_w_img, d_bias, d_out, rows, N, n_kv, st);
+    if (C == 64 && heads == 2) return launch_attn<64, 2>(d_x, d_kv, d_w_img, d_bias, d_out, rows, N, n_kv, st);
+    set_error("vit_attn_bf16: instantiated for (C, heads) = (32, 1) and (64, 2) (head dimension 32), got (%d, %d)", C, heads);
     return EVFLY_ERR_UNSUPPORTED;
 }

@@ -364,7 +364,11 @@ class OrigUNet(PackedModule):
         b = lambda name: getattr(self, "unet_" + name).bias
         cv = lambda g, name: tc.conv3x3(g, W[name], b(name), relu=True)
         cvp = lambda g, name: tc.conv3x3_pool(g, W[name], b(name), relu=True)     # conv + MaxPool2d(2), fused where it can be
-        y_e1, p1 = cvp(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12")
+        if self.form_BEV == 2 and tc.FUSE_STEM and tc.USE_HALO and tc.FUSE_POOL and im.shape[1] == 1:
+            # binary mask: unet_e11 is a 512-entry table lookup inside the e12 kernel, e11 never goes to HBM
+            y_e1, p1 = tc.stem_e12_pool(im, self.unet_e11.weight, self.unet_e11.bias, W["e12"], b("e12"))
+        else:
+            y_e1, p1 = cvp(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12")
         y_e2, p2 = cvp(cv(p1, "e21"), "e22")
         y_e3, p3 = cvp(cv(p2, "e31"), "e32")
         y_e4, p4 = cvp(cv(p3, "e41"), "e42")

@@ -373,3 +373,43 @@ def vit_ffn(tok, img, fbias, B, H, W, eps):
     _lib.check(_lib.load().evfly_vit_ffn_bf16(tok.data_ptr(), img.data_ptr(), _lib.ptr(fbias), out.data_ptr(), B, H, W, Cc, float(eps),
                                               _lib.stream_ptr()), "evfly_vit_ffn_bf16")
     return out
+
+
+FUSED_ATTN = True
+
+
+def pack_vit_attn(q_w, q_b, f_w, f_b):
+    """query / finalLayer weights [C, C] as pre-swizzled K-major operand images + their biases (fp32 [2C])."""
+    img = torch.cat([_kmajor_swizzled(q_w), _kmajor_swizzled(f_w)]).contiguous()
+    return img, torch.cat([q_b, f_b]).to(torch.float32).contiguous()
+
+
+def vit_attn(tok, kv, img, bias, heads):
+    """tok bf16 [B,N,C], kv bf16 [B,n_kv,2C] -> tok + finalLayer(attention(query(tok), kv)) bf16 [B,N,C], one launch."""
+    B, N, Cc = tok.shape
+    assert tok.is_contiguous() and kv.is_contiguous() and tok.dtype == BF16 and kv.dtype == BF16
+    out = torch.empty_like(tok)
+    _lib.check(_lib.load().evfly_vit_attn_bf16(tok.data_ptr(), kv.data_ptr(), img.data_ptr(), _lib.ptr(bias), out.data_ptr(), B, N, Cc, heads,
+                                               kv.shape[1], _lib.stream_ptr()), "evfly_vit_attn_bf16")
+    return out
+
+
+FUSE_STEM = True     # binary-input stem as a table lookup inside the e12 kernel (form_BEV = 2)
+
+
+def _call_stem_e12(*args):
+    _lib.check(_lib.load().evfly_tc_stem_e12_pool_bf16(*args, _lib.stream_ptr()), "evfly_tc_stem_e12_pool_bf16")
+
+
+def stem_e12_pool(mask_f32, stem_w, stem_b, w_packed, bias, relu=True):
+    """Binary mask [N,1,H,W] -> (y_e1 grid, pooled grid): unet_e11 + unet_e12 + MaxPool2d(2) without e11 in HBM."""
+    N, _, H, W = mask_f32.shape
+    dev = mask_f32.device
+    pat = torch.empty((N, H - 2, W - 2), dtype=torch.int16, device=dev)
+    _lib.check(_lib.load().evfly_stem_patterns(_lib.ptr(mask_f32), pat.data_ptr(), N, H, W, _lib.stream_ptr()), "evfly_stem_patterns")
+    out = new_grid(N, H, W, 32, H - 4, W - 4, dev)
+    ph, pw = (H - 4) // 2, (W - 4) // 2
+    pooled = new_grid(N, ph, pw, 32, ph, pw, dev)
+    _call_stem_e12(pat.data_ptr(), _lib.ptr(stem_w.contiguous()), _lib.ptr(stem_b), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(),
+                   pooled.data.data_ptr(), N, H, W, int(relu), pooled.Hp, pooled.Wp)
+    return out, pooled

@@ -546,6 +546,26 @@ int64_t evfly_vit_ffn_image_bytes(int C);
 int evfly_vit_ffn_bf16(const void* d_tokens, const void* d_w_img, const float* d_fbias, void* d_out, int B, int H, int W,
                        int C, float eps, void* stream);
 
+/* EfficientSelfAttention after the spatial reduction (ViTsubmodules.py:74-83) + the residual of :144 in one launch:
+ *   out = x + finalLayer(softmax(query(x) K^T / sqrt(d)) V)
+ * d_x / d_out bf16 [B, N, C]; d_kv bf16 [B, n_kv, 2C] = keyValueExtractor(LayerNorm(cn1(x))), layout [kv][head][d];
+ * d_w_img: pre-swizzled images of query.weight then finalLayer.weight (2*C*C*2 bytes, tc.pack_vit_attn);
+ * d_bias fp32: query bias [C], finalLayer bias [C]. (C, heads) = (32, 1) or (64, 2); n_kv <= 8.                 */
+int evfly_vit_attn_bf16(const void* d_x, const void* d_kv, const void* d_w_img, const float* d_bias, void* d_out, int64_t B,
+                        int N, int C, int heads, int n_kv, void* stream);
+
+/* Level 1 of OrigUNet for a BINARY input (form_BEV = 2, learner_models.py:489-491; every shipped configuration):
+ * unet_e11 (1 -> 32, 3x3 valid, bias, ReLU) has 2^9 possible outputs per pixel, so it runs as a table lookup inside
+ * the unet_e12 kernel and its output never exists in HBM (evfly_b200/csrc/tc_conv_halo.cu).
+ *   evfly_stem_patterns          mask fp32 [N,1,H,W] (0 / non-0) -> uint16 [N,H-2,W-2]: the 9 mask bits under each e11 pixel
+ *   evfly_tc_stem_e12_pool_bf16  patterns + unet_e11.{weight [32,1,3,3], bias} + packed unet_e12 weights / bias
+ *       -> y_e1 bf16 NHWC on the [N,H,W,32] pitch grid (valid (H-4) x (W-4)) and, when d_pool is given, MaxPool2d(2) of it
+ *       on the [N,Hp2,Wp2,32] grid (learner_models.py:533-535).                                                      */
+int evfly_stem_patterns(const float* d_mask, uint16_t* d_pat, int N, int H, int W, void* stream);
+int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w,
+                                const float* d_bias, void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2,
+                                int Wp2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,22 @@ def test_vit_tail_cat_and_same_padding_conv(cuda_lib):
     w2, b2 = bf(rnd(64, 64, 3, 3, seed=6, scale=(9 * 64) ** -0.5)), rnd(64, seed=7)
     got = tc.conv3x3_same(x.permute(0, 2, 3, 1).contiguous().to(BF).cuda(), tc.pack_conv3x3_weight(w2.cuda()), b2.cuda(), relu=True)
     check_bf16(got.permute(0, 3, 1, 2), F.relu(F.conv2d(x.double(), w2.double(), b2.double(), padding=1)), "same conv 64->64")
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 40, 52), (1, 260, 346), (3, 21, 13)])
+def test_stem_lookup_fused_into_e12(cuda_lib, N, H, W):
+    """Binary-mask stem as a table lookup inside the e12 kernel (learner_models.py:489-491,533-535) against PyTorch fp64
+    on the bf16-rounded weights, and against the two-kernel path (tensor-core stem, then e12 + pool)."""
+    g = torch.Generator().manual_seed(5)
+    mask = (torch.rand(N, 1, H, W, generator=g) < 0.35).float()
+    w1, b1 = rnd(32, 1, 3, 3, seed=1, scale=0.5), rnd(32, seed=2, scale=0.2)
+    w2, b2 = bf(rnd(32, 32, 3, 3, seed=3, scale=(9 * 32) ** -0.5)), rnd(32, seed=4, scale=0.1)
+    e11 = F.relu(F.conv2d(mask.double(), bf(w1).double(), b1.double())).to(BF).double()      # the kernel keeps e11 as bf16
+    want = F.relu(F.conv2d(e11, w2.double(), b2.double()))
+    out, pooled = tc.stem_e12_pool(mask.cuda(), w1.cuda(), b1.cuda(), tc.pack_conv3x3_weight(w2.cuda()), b2.cuda())
+    assert (out.vh, out.vw) == (H - 4, W - 4) and out.data.shape == (N, H, W, 32)
+    check_bf16(tc.grid_to_nchw(out.data, H - 4, W - 4), want, "stem+e12")
+    check_bf16(tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw), F.max_pool2d(want, 2), "stem+e12 pool")
+    ref_out, ref_pool = tc.conv3x3_pool(tc.stem_conv3x3(mask.cuda(), w1.cuda(), b1.cuda()), tc.pack_conv3x3_weight(w2.cuda()), b2.cuda())
+    d = (tc.grid_to_nchw(out.data, H - 4, W - 4) - tc.grid_to_nchw(ref_out.data, H - 4, W - 4)).abs()
+    assert d.max().item() <= 3e-2 and d.mean().item() <= 1e-3       # e11 values may differ by one bf16 ulp (summation order)

@@ -53,6 +53,27 @@ def test_fused_mixffn_block(cuda_lib, H, W, C, B):
     assert (got - exact).norm() / exact.norm() <= 1e-2
 
 
+@pytest.mark.parametrize("C,heads,N,n_kv", [(32, 1, 345, 2), (64, 2, 96, 6)])
+@pytest.mark.parametrize("B", [1, 5, 400])
+def test_fused_attention_block(cuda_lib, C, heads, N, n_kv, B):
+    """out = x + finalLayer(softmax(query(x) K^T / sqrt(d)) V) (ViTsubmodules.py:74-83,144) for given K, V."""
+    d = C // heads
+    x = bf(rnd(B, N, C, seed=1))
+    kv = bf(rnd(B, n_kv, 2 * C, seed=2))
+    wq, bq = bf(rnd(C, C, seed=3, scale=C ** -0.5)), rnd(C, seed=4, scale=0.1)
+    wf, bfin = bf(rnd(C, C, seed=5, scale=C ** -0.5)), rnd(C, seed=6, scale=0.1)
+    img, bias = tc.pack_vit_attn(wq.cuda(), bq.cuda(), wf.cuda(), bfin.cuda())
+    got = tc.vit_attn(x.to(BF).cuda(), kv.to(BF).cuda(), img, bias, heads).float().cpu().double()
+    q = (x.double() @ wq.double().t() + bq.double()).reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    kvr = kv.double().reshape(B, n_kv, 2, heads, d).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ kvr[0].transpose(-2, -1) / d ** 0.5, dim=-1) @ kvr[1]
+    att = att.transpose(1, 2).reshape(B, N, C).to(BF).double()                      # the kernel rounds the attention row to bf16
+    want = x.double() + att @ wf.double().t() + bfin.double()
+    err = (got - want).abs()
+    assert (err <= 2 ** -7 * want.abs() + 2e-2).all(), f"max err {err.max():.4g}"
+    assert err.mean() <= 2 ** -8 * want.abs().mean() + 1e-3
+
+
 def test_fused_path_equals_per_op_path_in_the_stage(cuda_lib):
     """A whole stage through encode_bf16 with the fused block and with the per-op launches it replaces."""
     import json, os
@@ -69,12 +90,12 @@ def test_fused_path_equals_per_op_path_in_the_stage(cuda_lib):
         t1, H1, W1 = m.encoder_blocks[0].encode_bf16(depth, True, 24, 60, 90)
         t2, _, _ = m.encoder_blocks[1].encode_bf16(t1, False, 24, H1, W1)
         old = tc.FUSED_FFN_MIN_BATCH
-        tc.FUSED_FFN_MIN_BATCH = 10 ** 9
+        tc.FUSED_FFN_MIN_BATCH, tc.FUSED_ATTN = 10 ** 9, False
         try:
             u1, _, _ = m.encoder_blocks[0].encode_bf16(depth, True, 24, 60, 90)
             u2, _, _ = m.encoder_blocks[1].encode_bf16(u1, False, 24, H1, W1)
         finally:
-            tc.FUSED_FFN_MIN_BATCH = old
+            tc.FUSED_FFN_MIN_BATCH, tc.FUSED_ATTN = old, True
     for a, b_, name in ((t1, u1, "stage 1"), (t2, u2, "stage 2")):
         d = (a.float() - b_.float()).abs()
         assert d.max().item() <= 0.15 and d.mean().item() <= 1e-2, (name, d.max().item(), d.mean().item())
