@@ -463,7 +463,7 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_w);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], kStemProducers);      // every producer thread arrives after its own proxy fence
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < Cfg::NACC; ++a) {
@@ -513,13 +513,30 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
             q0 = (y0 < EH && x0 < EW) ? (unsigned)__ldg(base + (long long)y0 * EW + x0) : 0u;
             q1 = (i1 < Cfg::HALO_ROWS && y1 < EH && x1 < EW) ? (unsigned)__ldg(base + (long long)y1 * EW + x1) : 0u;
         };
+        // the patterns of the next kDepth tiles are kept in flight (registers): a tile's two 2-byte loads come from HBM
+        // (~1 us), far longer than assembling a halo takes, and with one tile of lookahead that latency was the whole kernel
+        constexpr int kDepth = 4;
+        unsigned qa[kDepth], qb[kDepth];
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            qa[d] = qb[d] = 0;
+            const long long tl = (long long)blockIdx.x + (long long)d * gridDim.x;
+            if (tl < total_tiles) fetch((int)tl, qa[d], qb[d]);
+        }
         int stage = 0;
         uint32_t phase = 0;
-        unsigned q0 = 0, q1 = 0;
-        if ((int)blockIdx.x < total_tiles) fetch(blockIdx.x, q0, q1);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            unsigned n0 = 0, n1 = 0;
-            if (tile + (int)gridDim.x < total_tiles) fetch(tile + gridDim.x, n0, n1);      // next tile's patterns: in flight during this copy
+            const unsigned q0 = qa[0], q1 = qb[0];
+#pragma unroll
+            for (int d = 0; d + 1 < kDepth; ++d) {
+                qa[d] = qa[d + 1];
+                qb[d] = qb[d + 1];
+            }
+            qa[kDepth - 1] = qb[kDepth - 1] = 0;
+            {
+                const long long tl = (long long)tile + (long long)kDepth * gridDim.x;
+                if (tl < total_tiles) fetch((int)tl, qa[kDepth - 1], qb[kDepth - 1]);
+            }
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* dst = s_halo + stage * Cfg::HALO_BYTES;
             {
@@ -534,11 +551,8 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
 #pragma unroll
                 for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + i1 * 64 + ((c ^ sw) << 4)) = src[c];
             }
-            fence_proxy_async();                                                   // generic-proxy writes -> visible to tcgen05.mma
-            asm volatile("bar.sync 2, 96;" ::: "memory");                          // all producer threads have written and fenced
-            if (pt_id == 0) mbar_arrive(&full_bar[stage]);
-            q0 = n0;
-            q1 = n1;
+            fence_proxy_async();                                                   // this thread's generic-proxy writes -> visible to tcgen05.mma
+            mbar_arrive(&full_bar[stage]);                                         // the stage is full when all 96 producers have arrived
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
