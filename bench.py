@@ -340,6 +340,7 @@ class TrajectoryEvalWorkload:
             return wrapper
         for h in hooks:
             setattr(tc, h, timed(orig[h]))
+        stage_abi, tc.USE_STAGE_ABI = tc.USE_STAGE_ABI, False      # the same kernels enqueued one by one from Python, so that each can be timed
         try:
             with torch.no_grad():
                 self.pipe.reset()
@@ -351,6 +352,7 @@ class TrajectoryEvalWorkload:
                 n, T = self.N_TRAJ, self.T
                 self.model.forward_trajectories([tm, self.pipe._desvel(T * n), [None, None], None], n)
         finally:
+            tc.USE_STAGE_ABI = stage_abi
             for h in hooks:
                 setattr(tc, h, orig[h])
 

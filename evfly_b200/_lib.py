@@ -123,6 +123,18 @@ SIGNATURES.update({
     "evfly_lstm_seq_smemw": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
 })
 
+class UNetWeights(C.Structure):
+    """evfly_unet_weights (include/evfly_b200.h)."""
+    _fields_ = [("e11_w", _vp), ("e11_b", _vp), ("conv_w", _vp * 17), ("conv_b", _vp * 17), ("up_w", _vp * 4), ("up_b", _vp * 4),
+                ("out_w", _vp), ("out_b", _vp), ("lstm_wx", _vp), ("lstm_wh", _vp)]
+
+
+SIGNATURES.update({
+    "evfly_prep_frame": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "evfly_unet_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "evfly_unet_forward": (_i32, [C.POINTER(UNetWeights), _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+})
+
 ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "gelu": 3, "tanh": 4, "sigmoid": 5}
 
 _lib = None

@@ -10,21 +10,21 @@
 //
 //   pass 0  k_chunk_plan      one CTA: windows -> chunks of <= 8192 events (a chunk never straddles a window)
 //   pass 1  k_chunk_sort      one CTA per chunk: events -> registers (coalesced 8/16-byte loads, all in flight at
-//                             once), masks applied, band = row / rows_per_band; every warp ranks its events in a
-//                             PRIVATE per-band counter table with match.any + plain loads/stores (no atomics: a
-//                             shared-memory atomic with a return value costs ~4 clocks per event and was the whole
-//                             kernel), the tables are prefix-summed, counting sort in shared memory, the chunk
-//                             written back as compact 8-byte records ordered by band + the chunk's band offsets.
-//                             No global atomics, no inter-CTA dependency.
+//                             once), masks applied, band = row / rows_per_band ranked with ONE shared-memory
+//                             atomic per event, counting sort in shared memory, the chunk written back as compact
+//                             8-byte records ordered by band + the chunk's band offsets. No global atomics, no
+//                             inter-CTA dependency.
 //   pass 2  k_band_accumulate one CTA per (band, window): the band's 2 + B planes live in shared memory; the CTA
 //                             walks the band's piece of every chunk of its window (each event read once, from L2
 //                             when pass 1 has just written it), shared-memory atomics, coalesced write-out.
 //                             Nothing is zero-filled in HBM and counts are exact integers whatever the order.
-//                             Voxel bins accumulate in FIXED POINT (2^-24, a 32-bit low word updated with the native
-//                             integer atomic + a carry word): sm_100 has no native shared-memory fp32 (or 64-bit)
-//                             atomic add -- both compile to CAS spin loops -- and the integer sum is exact and
-//                             order-independent: the fp32 result is the correctly rounded sum of the 2^-24-quantised
-//                             weights, bit-reproducible from run to run, with sum_b V[b] = n+ - n- exactly.
+//
+// Measured dead ends (B200, 10 M events @480x640; profiles/r2_accumulate_variants.txt): ranking pass 1 with match.any
+// and per-warp counter tables instead of one shared-memory atomic per event: 77 -> 150 us (MATCH.ANY is slow and the
+// 16 batches of a warp serialise); accumulating the voxel bins as 2^-24 fixed point with the native 32-bit integer
+// atomic + a carry word instead of atomicAdd(float) (a CAS spin loop in SASS, sm_100 has no shared-memory fp32 or
+// 64-bit add): pass 2 88 -> 113 us (one window) and 270 -> 483 us (100 windows: 48 instead of 28 bytes of shared
+// memory per pixel mean more, smaller bands). Both were reverted.
 //
 // Algorithmic bytes: record_bytes * events + 4*(2+B)*H*W per window. Extra traffic: 8 B per event written and read
 // once more (the sorted copy; L2-resident for up to ~10 M events).
@@ -48,11 +48,8 @@ struct BandGeom {
     size_t smem;         // pass-2 dynamic shared memory
 };
 
-// bytes of shared memory per pixel of a band: two int32 counts + B int64 fixed-point voxel bins
-static inline int pixel_bytes(int B) { return 8 + 8 * B; }
-
-static inline bool band_geometry(int H, int W, int B, int n_windows, BandGeom* g) {
-    const long long per_row = (long long)pixel_bytes(B) * W;
+static inline bool band_geometry(int H, int W, int planes, int n_windows, BandGeom* g) {
+    const long long per_row = 4ll * planes * W;
     if (per_row > 200 * 1024) return false;
     long long rows_cap = (100 * 1024) / per_row;            // two CTAs per SM when the band allows it
     if (rows_cap < 1) rows_cap = 1;
@@ -132,7 +129,6 @@ k_chunk_sort(const void* __restrict__ records, const int64_t* __restrict__ win_o
              const int* __restrict__ chunk_first, int max_chunks, uint2* __restrict__ sorted, int* __restrict__ table_t) {
     extern __shared__ __align__(16) uint2 s_sorted[];     // [kChunk]
     __shared__ int s_hist[kMaxBands + 1];
-    __shared__ int s_wh[(kSortThreads / 32) * (kMaxBands + 1)];     // per-warp band counters, then per-warp offsets inside the band
     __shared__ int s_warp[kSortThreads / 32];
     __shared__ int s_w;
     const int c = blockIdx.x;
@@ -145,6 +141,7 @@ k_chunk_sort(const void* __restrict__ records, const int64_t* __restrict__ win_o
         }
         s_w = lo;
     }
+    for (int b = threadIdx.x; b <= bands; b += kSortThreads) s_hist[b] = 0;
     __syncthreads();
     const int w = s_w;
     const int64_t ebeg = win_offsets[w] + (int64_t)(c - chunk_first[w]) * kChunk;
@@ -189,45 +186,18 @@ k_chunk_sort(const void* __restrict__ records, const int64_t* __restrict__ win_o
             w1[u] = (uint32_t)dt;
         }
     }
-    // ---- rank inside (warp, band): events u*512 + t of a fixed u are 32 consecutive events per warp; lanes with the same
-    // band find each other with match.any, the group's first lane bumps the warp's PRIVATE counter with a plain store
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        int* wh = s_wh + warp * (kMaxBands + 1);
-        for (int b = lane; b <= bands; b += 32) wh[b] = 0;
-        __syncwarp();
-        const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-        for (int u = 0; u < kEPT; ++u) {
-            const bool ok = key[u] != 0xffffffffu;
-            unsigned band = (unsigned)bands;                  // dropped events share the spare slot
-            if (ok) {
-                const unsigned y = key[u];
-                band = rows > 1 ? __umulhi(y, magic) : y;     // exact for y < 2^16 (magic = floor(2^32/rows) + 1)
-                w0[u] |= (y - band * rows) << 16;
-            }
-            const unsigned grp = __match_any_sync(0xffffffffu, band);
-            const int old = wh[band];
-            __syncwarp();
-            if ((grp & lt) == 0u) wh[band] = old + __popc(grp);
-            __syncwarp();
-            if (ok) key[u] = (band << 16) | (unsigned)(old + __popc(grp & lt));
+    for (int u = 0; u < kEPT; ++u) {
+        if (key[u] != 0xffffffffu) {
+            const unsigned y = key[u];
+            const unsigned band = rows > 1 ? __umulhi(y, magic) : y;     // exact for y < 2^16 (magic = floor(2^32/rows) + 1)
+            w0[u] |= (y - band * rows) << 16;
+            const int rank = atomicAdd(&s_hist[band], 1);
+            key[u] = (band << 16) | (unsigned)rank;
         }
     }
     __syncthreads();
-    // per band: exclusive prefix over the warps (in place) and the band total
-    if ((int)threadIdx.x <= bands) {
-        int run = 0;
-#pragma unroll
-        for (int w = 0; w < kSortThreads / 32; ++w) {
-            const int c = s_wh[w * (kMaxBands + 1) + threadIdx.x];
-            s_wh[w * (kMaxBands + 1) + threadIdx.x] = run;
-            run += c;
-        }
-        s_hist[threadIdx.x] = (int)threadIdx.x < bands ? run : 0;       // the spare slot (dropped events) counts for nothing
-    }
-    __syncthreads();
-    // exclusive scan of s_hist[0..bands] (bands <= 511: one element per thread)
+    // exclusive scan of s_hist[0..bands] (bands <= 512 = one element per thread)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int v = (int)threadIdx.x <= bands ? s_hist[threadIdx.x] : 0;
@@ -253,15 +223,9 @@ k_chunk_sort(const void* __restrict__ records, const int64_t* __restrict__ win_o
         if ((int)threadIdx.x <= bands) s_hist[threadIdx.x] = s_warp[warp] + incl - v;
     }
     __syncthreads();
-    {
-        const int* wh = s_wh + (threadIdx.x >> 5) * (kMaxBands + 1);
 #pragma unroll
-        for (int u = 0; u < kEPT; ++u)
-            if (key[u] != 0xffffffffu) {
-                const unsigned band = key[u] >> 16;
-                s_sorted[s_hist[band] + wh[band] + (int)(key[u] & 0xffffu)] = make_uint2(w0[u], w1[u]);
-            }
-    }
+    for (int u = 0; u < kEPT; ++u)
+        if (key[u] != 0xffffffffu) s_sorted[s_hist[key[u] >> 16] + (int)(key[u] & 0xffffu)] = make_uint2(w0[u], w1[u]);
     __syncthreads();
     const int total = s_hist[bands];
     uint2* out = sorted + ebeg;
@@ -285,11 +249,10 @@ k_band_accumulate(const uint2* __restrict__ sorted, const int64_t* __restrict__ 
     const unsigned rows = min(rows_per_band, H - y0);
     const unsigned npx = rows * W;
     const unsigned plane = rows_per_band * W;
-    int* s_cnt = reinterpret_cast<int*>(s_raw);                                              // [2][plane]
-    unsigned* s_vlo = reinterpret_cast<unsigned*>(s_raw) + 2 * plane;                          // [B][plane] low word, units of 2^-24
-    int* s_vhi = reinterpret_cast<int*>(s_raw) + (2 + B) * plane;                              // [B][plane] carries (units of 2^8)
+    int* s_cnt = reinterpret_cast<int*>(s_raw);                     // [2][plane]
+    float* s_vox = reinterpret_cast<float*>(s_raw) + 2 * plane;     // [B][plane]
     {
-        const unsigned words = (2 + (has_voxel ? 2 * B : 0)) * plane;
+        const unsigned words = (2 + (has_voxel ? B : 0)) * plane;
         uint4* z = reinterpret_cast<uint4*>(s_raw);
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         for (unsigned i = threadIdx.x; i < (words + 3) / 4; i += blockDim.x) z[i] = zero;
@@ -363,22 +326,19 @@ k_band_accumulate(const uint2* __restrict__ sorted, const int64_t* __restrict__ 
                 const unsigned x = e[j].x & 0xffffu, yy = (e[j].x >> 16) & 0x7fffu, pol = e[j].x >> 31;
                 const unsigned pix = yy * W + x;
                 atomicAdd(s_cnt + pol * plane + pix, 1);
-                if (has_voxel && B > 1) {
-                    // tau in fp64 like voxel_weights() of accumulate.cu; the two weights in units of 2^-24, w_lo + w_hi = 1 exactly
-                    const double tau = (double)e[j].y * scale;
-                    int s = (int)tau;
-                    if (s > B - 2) s = B - 2;
-                    if (s < 0) s = 0;
-                    const unsigned w_hi = (unsigned)__double2int_rn((tau - (double)s) * 16777216.0);
-                    const unsigned w_lo = 16777216u - w_hi;
-                    unsigned* lo0 = s_vlo + (unsigned)s * plane + pix;
-                    int* hi0 = s_vhi + (unsigned)s * plane + pix;
-                    if (pol) {
-                        if (w_lo) { const unsigned old = atomicAdd(lo0, w_lo); if (old + w_lo < old) atomicAdd(hi0, 1); }
-                        if (w_hi) { const unsigned old = atomicAdd(lo0 + plane, w_hi); if (old + w_hi < old) atomicAdd(hi0 + plane, 1); }
+                if (has_voxel) {
+                    const float sgn = pol ? 1.0f : -1.0f;
+                    if (B == 1) {
+                        atomicAdd(s_vox + pix, sgn);
                     } else {
-                        if (w_lo) { const unsigned old = atomicAdd(lo0, 0u - w_lo); if (old < w_lo) atomicAdd(hi0, -1); }
-                        if (w_hi) { const unsigned old = atomicAdd(lo0 + plane, 0u - w_hi); if (old < w_hi) atomicAdd(hi0 + plane, -1); }
+                        // identical arithmetic to voxel_weights() of accumulate.cu: tau in fp64, weights rounded once
+                        const double tau = (double)e[j].y * scale;
+                        int s = (int)tau;
+                        if (s > B - 2) s = B - 2;
+                        if (s < 0) s = 0;
+                        const double f = tau - (double)s;
+                        atomicAdd(s_vox + (unsigned)s * plane + pix, sgn * (float)(1.0 - f));
+                        atomicAdd(s_vox + (unsigned)(s + 1) * plane + pix, sgn * (float)f);
                     }
                 }
             }
@@ -395,13 +355,8 @@ k_band_accumulate(const uint2* __restrict__ sorted, const int64_t* __restrict__ 
     }
     if (has_voxel) {
         float* vw = voxel + slot * B * HW + band0;
-        if (B == 1) {       // one bin: V = n+ - n-
-            for (unsigned i = threadIdx.x; i < npx; i += blockDim.x) vw[i] = (float)(s_cnt[plane + i] - s_cnt[i]);
-        } else {
-            for (int b = 0; b < B; ++b)
-                for (unsigned i = threadIdx.x; i < npx; i += blockDim.x)
-                    vw[(size_t)b * HW + i] = (float)(((double)s_vhi[(unsigned)b * plane + i] * 4294967296.0 + (double)s_vlo[(unsigned)b * plane + i]) * (1.0 / 16777216.0));
-        }
+        for (int b = 0; b < B; ++b)
+            for (unsigned i = threadIdx.x; i < npx; i += blockDim.x) vw[(size_t)b * HW + i] = s_vox[(unsigned)b * plane + i];
     }
 }
 
@@ -464,7 +419,7 @@ template <bool REC16>
 static int run_sorted(const void* recs, int64_t n, const int64_t* offs, const int64_t* t0, const int64_t* t1, const int* out_slot, int slot_stride,
                       int slot_offset, int n_windows, int H, int W, int B, int32_t* counts, float* voxel, void* ws, int64_t ws_bytes, cudaStream_t st) {
     BandGeom g;
-    EVFLY_REQUIRE(band_geometry(H, W, voxel ? B : 0, n_windows, &g), "accumulate_windows (tiled): a row of %d pixels x %d planes does not fit shared memory", W, 2 + B);
+    EVFLY_REQUIRE(band_geometry(H, W, 2 + (voxel ? B : 0), n_windows, &g), "accumulate_windows (tiled): a row of %d pixels x %d planes does not fit shared memory", W, 2 + B);
     EVFLY_REQUIRE(n <= (1ll << 40), "accumulate_windows (tiled): too many events");
     if (ws_bytes < sorted_ws_bytes(n, n_windows, g.bands)) {
         set_error("accumulate_windows (tiled): workspace of %lld bytes, %lld needed", (long long)ws_bytes, (long long)sorted_ws_bytes(n, n_windows, g.bands));
@@ -500,7 +455,7 @@ static inline bool dims_ok_t(int H, int W) { return H > 0 && W > 0 && H <= 32767
 extern "C" int64_t evfly_accumulate_sorted_workspace_bytes(int64_t n, int n_windows, int H, int W, int B) {
     // the band count only shrinks when the voxel planes are dropped or more windows are given: size for the largest
     BandGeom g;
-    if (n < 0 || n_windows < 0 || !dims_ok_t(H, W) || B < 0 || !band_geometry(H, W, B, 1, &g)) return 0;
+    if (n < 0 || n_windows < 0 || !dims_ok_t(H, W) || B < 0 || !band_geometry(H, W, 2 + B, 1, &g)) return 0;
     return sorted_ws_bytes(n, n_windows, g.bands) + align_up(8ll * (n_windows + 1), 256) + 256;   // + the window ranges of the 16-byte entry point
 }
 

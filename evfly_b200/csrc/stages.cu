@@ -1,0 +1,297 @@
+// stages.cu -- STAGE-LEVEL entry points of the C ABI: whole stages of the hot path enqueued from C++
+// on the caller's stream, so a host in any language (the C++ side of evfly_ros, a C test) drives the path with a
+// handful of calls and the whole step is capturable in one CUDA graph:
+//
+//   evfly_prep_frame      u8 node frame or int32 count frames -> decode, centre crop, 97th-percentile scale, clip
+//                         (evfly_ros/run.py:334-350, 250-253)
+//   evfly_unet_forward    OrigUNet.forward in the shipped configuration (learner/learner_models.py:521-585 with
+//                         form_BEV = 2, skip_type = interp, one 1x1 ConvLSTM layer; learner/configs/*.txt:39-47):
+//                         normalised frames -> depth map + y_upconv + ConvLSTM state
+//   evfly_vit_lstm_forward  LSTMNetVIT.forward (learner/vitfly_models.py:132-150): depth -> velocity commands + LSTM state
+//
+// Weights arrive PACKED (the layouts of evfly_b200/tc.py's pack_* helpers, restated in include/evfly_b200.h) in
+// caller-owned device memory; every intermediate lives in a caller-owned workspace (evfly_*_workspace_bytes);
+// nothing is allocated, nothing synchronises. The functions below only SEQUENCE the operator entry points of this
+// library -- the arithmetic is exactly the one of the Python drop-in modules, which call these when the model is in
+// the shipped configuration.
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <string.h>
+
+namespace evfly {
+
+struct Bump {
+    uint8_t* p;
+    int64_t left;
+    bool ok = true;
+    void* take(int64_t bytes) {
+        const int64_t b = (bytes + 255) / 256 * 256;
+        if (b > left) {
+            ok = false;
+            return nullptr;
+        }
+        void* r = p;
+        p += b;
+        left -= b;
+        return r;
+    }
+};
+
+// fp32 state [n, Ch, vh, vw] (NCHW) -> fp32 pitch grid [n, Hp, Wp, Ch] (zero outside the valid region) and back
+__global__ void __launch_bounds__(256)
+k_state_nchw_to_grid(const float* __restrict__ src, float* __restrict__ dst, int n, int Ch, int vh, int vw, int Hp, int Wp) {
+    const long long total = (long long)n * Hp * Wp * Ch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Ch);
+        const long long pix = i / Ch;
+        const int x = (int)(pix % Wp), y = (int)((pix / Wp) % Hp);
+        const long long b = pix / ((long long)Wp * Hp);
+        dst[i] = (y < vh && x < vw) ? src[((b * Ch + c) * vh + y) * vw + x] : 0.f;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_state_grid_to_nchw(const float* __restrict__ src, float* __restrict__ dst, int n, int Ch, int vh, int vw, int Hp, int Wp) {
+    const long long total = (long long)n * Ch * vh * vw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % vw), y = (int)((i / vw) % vh);
+        const int c = (int)((i / ((long long)vw * vh)) % Ch);
+        const long long b = i / ((long long)vw * vh * Ch);
+        dst[i] = src[((b * Hp + y) * Wp + x) * (long long)Ch + c];
+    }
+}
+
+struct UNetGeom {
+    int Hp[5], Wp[5];      // pitch grid of level l (level 0 = the input frame)
+    int ev[5][2];          // valid extent of the level's second conv output (y_e{l+1})
+    bool ok;
+};
+
+static UNetGeom unet_geometry(int H, int W) {
+    UNetGeom g;
+    g.ok = true;
+    int h = H, w = W;
+    for (int l = 0; l < 5; ++l) {
+        g.Hp[l] = h;
+        g.Wp[l] = w;
+        g.ev[l][0] = h - 4;
+        g.ev[l][1] = w - 4;
+        if (h - 4 < 2 || w - 4 < 2) g.ok = false;
+        h = (h - 4) / 2;
+        w = (w - 4) / 2;
+    }
+    return g;
+}
+
+static inline bool halo_ok(int cin, int cout) {
+    return ((cin == 32 || cin == 64) && (cout == 32 || cout == 64)) || (cin == 64 && cout == 128) || (cin == 128 && (cout == 64 || cout == 128 || cout == 256));
+}
+
+// 3x3 valid conv + bias + ReLU on the pitch grid (+ optional MaxPool2d(2) of the result), the dispatch of tc.conv3x3(_pool)
+static int conv3(const void* x, int N, int Hp, int Wp, int vh, int vw, int Cin, const void* w, const float* b, int Cout, void* out, void* pool,
+                 int Hp2, int Wp2, void* st) {
+    if (halo_ok(Cin, Cout)) {
+        if (pool) return evfly_tc_conv3x3_halo_pool_bf16(x, w, b, out, pool, N, Hp, Wp, vh, vw, Cin, Cout, 1, Hp2, Wp2, st);
+        return evfly_tc_conv3x3_halo_bf16(x, w, b, out, N, Hp, Wp, vh, vw, Cin, Cout, 1, st);
+    }
+    evfly_tc_conv_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = x;
+    a.w = w;
+    a.bias = b;
+    a.out = out;
+    a.M_rows = (int64_t)N * Hp * Wp;
+    a.out_ld = Cout;
+    a.Cin = Cin;
+    a.n_rows = Cout;
+    a.taps = 9;
+    a.w_pitch = Wp;
+    a.relu = 1;
+    int rc = evfly_tc_conv_bf16(&a, st);
+    if (!rc && pool) rc = evfly_maxpool2x2_nhwc_bf16(out, pool, N, Hp, Wp, vh - 2, vw - 2, Cout, st);
+    return rc;
+}
+
+static int gemm_f32out(const void* x, int64_t M, int K, const void* w, const float* bias, int Nn, float* out, void* st) {
+    evfly_tc_conv_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = x;
+    a.w = w;
+    a.bias = bias;
+    a.out_f32 = out;
+    a.M_rows = M;
+    a.out_ld = Nn;
+    a.Cin = K;
+    a.n_rows = Nn;
+    a.taps = 1;
+    return evfly_tc_conv_bf16(&a, st);
+}
+
+static int convt2x2(const void* x, int N, int Hp, int Wp, int vh, int vw, int Cin, const void* w, const float* b, int Cout, void* out, int out_ld,
+                    int out_c0, void* st) {
+    evfly_tc_conv_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = x;
+    a.w = w;
+    a.bias = b;
+    a.out = out;
+    a.M_rows = (int64_t)N * Hp * Wp;
+    a.out_ld = out_ld;
+    a.Cin = Cin;
+    a.n_rows = 4 * Cout;
+    a.taps = 1;
+    a.out_c0 = out_c0;
+    a.convt = 1;
+    a.Hp = Hp;
+    a.Wp = Wp;
+    a.valid_h = vh;
+    a.valid_w = vw;
+    a.cout_t = Cout;
+    return evfly_tc_conv_bf16(&a, st);
+}
+
+static const int kEncC[6] = {1, 32, 64, 128, 256, 512};
+
+}  // namespace evfly
+
+using namespace evfly;
+
+#define RC(call)                \
+    do {                        \
+        const int rc__ = (call); \
+        if (rc__) return rc__;  \
+    } while (0)
+
+extern "C" int evfly_prep_frame(const uint8_t* d_u8, const int32_t* d_counts, int N, int H, int W, int h, int w, float* d_frames, void* stream) {
+    EVFLY_REQUIRE((d_u8 != nullptr) != (d_counts != nullptr), "prep_frame: give either the u8 node frames or the int32 count frames");
+    EVFLY_REQUIRE(d_frames && N >= 0 && h <= H && w <= W, "prep_frame: bad argument");
+    if (N == 0) return EVFLY_OK;
+    if (d_counts)      // integer counts: decode + crop + exact percentile + clip in one kernel
+        return evfly_counts_normalise(d_counts, N, H, W, h, w, 0.2f, 0.97f, -1.0f, 1.0f, 0.0f, d_frames, nullptr, stream);
+    RC(evfly_decode_crop(d_u8, nullptr, N, H, W, h, w, 0.2f, d_frames, stream));
+    return evfly_quantile_scale_clip(d_frames, N, (int64_t)h * w, 0.97f, -1.0f, 1.0f, 0.0f, d_frames, nullptr, stream);
+}
+
+extern "C" int64_t evfly_unet_workspace_bytes(int N, int n_traj, int H, int W) {
+    const UNetGeom g = unet_geometry(H, W);
+    if (!g.ok || N <= 0 || n_traj <= 0 || N % n_traj) return 0;
+    int64_t total = 4096;
+    auto add = [&](int64_t b) { total += (b + 255) / 256 * 256; };
+    add((int64_t)N * H * W * 4);                      // mask
+    add((int64_t)N * (H - 2) * (W - 2) * 2);          // stem patterns
+    for (int l = 0; l < 5; ++l) {
+        const int64_t px = (int64_t)N * g.Hp[l] * g.Wp[l];
+        if (l > 0) add(px * kEncC[l] * 2);            // pooled input of the level
+        if (l > 0) add(px * kEncC[l + 1] * 2);        // first conv
+        add(px * kEncC[l + 1] * 2);                   // second conv (y_e)
+    }
+    const int64_t P5 = (int64_t)N * g.Hp[4] * g.Wp[4];
+    add(P5 * 2048 * 4);                               // x gates
+    add((P5 + P5 / (N / n_traj)) * 512 * 2);          // h_all
+    add(P5 / (N / n_traj) * 512 * 4);                 // c
+    add(256);                                         // scan barrier
+    int vh = g.ev[4][0], vw = g.ev[4][1];
+    for (int lvl = 1; lvl <= 4; ++lvl) {
+        const int C = kEncC[5 - lvl];
+        const int64_t px = (int64_t)N * (2 * vh) * (2 * vw);
+        add(px * 2 * C * 2);                          // cat
+        add(px * C * 2);                              // d_l1
+        add(px * C * 2);                              // d_l2
+        vh = 2 * vh - 4;
+        vw = 2 * vw - 4;
+    }
+    add((int64_t)N * (vh + 4) * (vw + 4) * 4);        // out32
+    return total;
+}
+
+extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames, int N, int n_traj, int H, int W, float cutoff, const float* d_h0,
+                                  const float* d_c0, float* d_hT, float* d_cT, float* d_depth, float* d_y_upconv, void* d_ws, int64_t ws_bytes,
+                                  void* stream) {
+    EVFLY_REQUIRE(wts && d_frames && d_depth && d_y_upconv && d_ws && N > 0 && n_traj > 0 && N % n_traj == 0, "unet_forward: bad argument");
+    EVFLY_REQUIRE((d_h0 == nullptr) == (d_c0 == nullptr), "unet_forward: h0 / c0 go together");
+    const UNetGeom g = unet_geometry(H, W);
+    EVFLY_REQUIRE(g.ok, "unet_forward: a %dx%d frame is too small for the 5-level UNet", H, W);
+    const int64_t need = evfly_unet_workspace_bytes(N, n_traj, H, W);
+    if (ws_bytes < need) {
+        set_error("unet_forward: workspace of %lld bytes, %lld needed", (long long)ws_bytes, (long long)need);
+        return EVFLY_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Bump ws{reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~(uintptr_t)255), ws_bytes - 256};
+    const int T = N / n_traj;
+
+    // ---- form_input (learner_models.py:476-494, form_BEV = 2): in place on the caller's frames, mask out
+    float* mask = (float*)ws.take((int64_t)N * H * W * 4);
+    RC(evfly_form_input_f32(d_frames, mask, (int64_t)N * H * W, (int64_t)H * W, 2, cutoff, stream));
+    // ---- encoder (learner_models.py:533-541)
+    void* ye[5];
+    {
+        uint16_t* pat = (uint16_t*)ws.take((int64_t)N * (H - 2) * (W - 2) * 2);
+        RC(evfly_stem_patterns(mask, pat, N, H, W, stream));
+        ye[0] = ws.take((int64_t)N * H * W * 32 * 2);
+        void* pooled = ws.take((int64_t)N * g.Hp[1] * g.Wp[1] * 32 * 2);
+        RC(evfly_tc_stem_e12_pool_bf16(pat, wts->e11_w, wts->e11_b, wts->conv_w[0], wts->conv_b[0], ye[0], pooled, N, H, W, 1, g.Hp[1], g.Wp[1], stream));
+        const void* x = pooled;
+        for (int l = 1; l < 5; ++l) {
+            const int Hp = g.Hp[l], Wp = g.Wp[l], Cin = kEncC[l], C = kEncC[l + 1];
+            const int64_t px = (int64_t)N * Hp * Wp;
+            void* c1 = ws.take(px * C * 2);
+            ye[l] = ws.take(px * C * 2);
+            void* nxt = l < 4 ? ws.take((int64_t)N * g.Hp[l + 1] * g.Wp[l + 1] * C * 2) : nullptr;
+            RC(conv3(x, N, Hp, Wp, Hp, Wp, Cin, wts->conv_w[2 * l - 1], wts->conv_b[2 * l - 1], C, c1, nullptr, 0, 0, stream));
+            RC(conv3(c1, N, Hp, Wp, Hp - 2, Wp - 2, C, wts->conv_w[2 * l], wts->conv_b[2 * l], C, ye[l], nxt, l < 4 ? g.Hp[l + 1] : 0, l < 4 ? g.Wp[l + 1] : 0, stream));
+            x = nxt;
+        }
+    }
+    // ---- ConvLSTM over time (learner_models.py:544-546; convlstm.py:136-176), n_traj trajectories side by side
+    const int Hp5 = g.Hp[4], Wp5 = g.Wp[4], vh5 = g.ev[4][0], vw5 = g.ev[4][1], Ch = 512;
+    const int64_t P = (int64_t)n_traj * Hp5 * Wp5;
+    float* gx = (float*)ws.take((int64_t)T * P * 4 * Ch * 4);
+    __nv_bfloat16* h_all = (__nv_bfloat16*)ws.take((int64_t)(T + 1) * P * Ch * 2);
+    float* cst = (float*)ws.take(P * Ch * 4);
+    void* sync = ws.take(256);
+    EVFLY_REQUIRE(ws.ok, "unet_forward: workspace exhausted (internal sizing error)");
+    RC(gemm_f32out(ye[4], (int64_t)T * P, Ch, wts->lstm_wx, nullptr, 4 * Ch, gx, stream));
+    if (d_h0) {
+        RC(evfly_nchw_f32_to_nhwc_bf16(d_h0, h_all, n_traj, Ch, vh5, vw5, Hp5, Wp5, stream));
+        k_state_nchw_to_grid<<<stream_grid(P * Ch, 256, 8), 256, 0, st>>>(d_c0, cst, n_traj, Ch, vh5, vw5, Hp5, Wp5);
+        EVFLY_LAUNCHED();
+    } else {
+        EVFLY_CUDA(cudaMemsetAsync(h_all, 0, P * Ch * 2, st));
+        EVFLY_CUDA(cudaMemsetAsync(cst, 0, P * Ch * 4, st));
+    }
+    RC(evfly_convlstm_scan_bf16(h_all, wts->lstm_wh, gx, cst, T, P, Ch, sync, stream));
+    if (d_hT) RC(evfly_nhwc_to_nchw_f32(h_all + (int64_t)T * P * Ch, 0, d_hT, n_traj, Ch, vh5, vw5, Hp5, Wp5, stream));
+    if (d_cT) {
+        k_state_grid_to_nchw<<<stream_grid((int64_t)n_traj * Ch * vh5 * vw5, 256, 8), 256, 0, st>>>(cst, d_cT, n_traj, Ch, vh5, vw5, Hp5, Wp5);
+        EVFLY_LAUNCHED();
+    }
+    // ---- decoder (learner_models.py:553-585): bilinear skip || ConvTranspose2d(2,2) -> cat -> two 3x3 convs
+    const void* y = h_all + P * Ch;       // h_1 .. h_T = the ConvLSTM output sequence, frame t*n_traj + s
+    int yHp = Hp5, yWp = Wp5, yvh = vh5, yvw = vw5;
+    for (int lvl = 1; lvl <= 4; ++lvl) {
+        const int C = kEncC[5 - lvl], Cin = kEncC[6 - lvl];
+        const int oh = 2 * yvh, ow = 2 * yvw;
+        const int64_t px = (int64_t)N * oh * ow;
+        void* cat = ws.take(px * 2 * C * 2);
+        void* d1 = ws.take(px * C * 2);
+        void* d2 = ws.take(px * C * 2);
+        EVFLY_REQUIRE(ws.ok, "unet_forward: workspace exhausted (internal sizing error)");
+        const int el = 4 - lvl;           // encoder level whose output is skipped in
+        RC(evfly_resize_bilinear_nhwc_bf16(ye[el], cat, N, g.Hp[el], g.Wp[el], g.ev[el][0], g.ev[el][1], C, oh, ow, 2 * C, 0, stream));
+        RC(convt2x2(y, N, yHp, yWp, yvh, yvw, Cin, wts->up_w[lvl - 1], wts->up_b[lvl - 1], C, cat, 2 * C, C, stream));
+        RC(conv3(cat, N, oh, ow, oh, ow, 2 * C, wts->conv_w[9 + 2 * (lvl - 1)], wts->conv_b[9 + 2 * (lvl - 1)], C, d1, nullptr, 0, 0, stream));
+        RC(conv3(d1, N, oh, ow, oh - 2, ow - 2, C, wts->conv_w[10 + 2 * (lvl - 1)], wts->conv_b[10 + 2 * (lvl - 1)], C, d2, nullptr, 0, 0, stream));
+        y = d2;
+        yHp = oh;
+        yWp = ow;
+        yvh = oh - 4;
+        yvw = ow - 4;
+    }
+    // ---- 1x1 output conv (:583) and the bilinear resize back to the input size (:497)
+    float* out32 = (float*)ws.take((int64_t)N * yHp * yWp * 4);
+    EVFLY_REQUIRE(ws.ok, "unet_forward: workspace exhausted (internal sizing error)");
+    RC(gemm_f32out(y, (int64_t)N * yHp * yWp, 32, wts->out_w, wts->out_b, 1, out32, stream));
+    RC(evfly_nhwc_to_nchw_f32(out32, 1, d_y_upconv, N, 1, yvh, yvw, yHp, yWp, stream));
+    const int64_t xs[4] = {(int64_t)yvh * yvw, (int64_t)yvh * yvw, yvw, 1}, ys[4] = {(int64_t)H * W, (int64_t)H * W, W, 1};
+    return evfly_resize_bilinear_f32(d_y_upconv, xs, d_depth, ys, N, 1, yvh, yvw, H, W, 0, 1.0f, 0.0f, -INFINITY, INFINITY, stream);
+}

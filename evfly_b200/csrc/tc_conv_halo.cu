@@ -463,7 +463,7 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_w);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full_bar[s], kStemProducers);      // every producer thread arrives after its own proxy fence
+            mbar_init(&full_bar[s], kStemProducers / 32); // one arrival per producer warp, after every lane's proxy fence
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < Cfg::NACC; ++a) {
@@ -552,7 +552,8 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
                 for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + i1 * 64 + ((c ^ sw) << 4)) = src[c];
             }
             fence_proxy_async();                                                   // this thread's generic-proxy writes -> visible to tcgen05.mma
-            mbar_arrive(&full_bar[stage]);                                         // the stage is full when all 96 producers have arrived
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);                          // the stage is full when the three producer warps have arrived
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {

@@ -290,7 +290,69 @@ class OrigUNet(PackedModule):
                 w2 = w.reshape(w.shape[0], -1)      # 1x1 kernel; rows gate-major -> interleaved (fused cell epilogue)
                 bf["lstm"].append((tc.pack_convlstm_gate_weight(w2[:, :cell.input_dim]), tc.pack_convlstm_gate_weight(w2[:, cell.input_dim:])))
         pk["bf16"] = bf
+        pk["stage"] = self._pack_stage(bf) if self._stage_ok() and self.unet_e11.weight.is_cuda else None
         return pk
+
+    # ---- stage-level C ABI (csrc/stages.cu): the whole forward enqueued by ONE call -------------------
+    def _stage_ok(self):
+        """The shipped configuration (learner/configs/*.txt:39-47), for which evfly_unet_forward is written."""
+        return (self.form_BEV == 2 and self.skip_type == 'interp' and self.num_in_channels == 1 and self.num_out_channels == 1 and self.velpred == 0
+                and not self.is_deployment and list(self.num_recurrent)[0] == 1)
+
+    def _pack_stage(self, bf):
+        from . import _lib
+        w = _lib.UNetWeights()
+        keep = []           # tensors the struct points into
+
+        def p(t):
+            t = t.contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        w.e11_w, w.e11_b = p(self.unet_e11.weight.float()), p(self.unet_e11.bias.float())
+        for i, name in enumerate(("e12", "e21", "e22", "e31", "e32", "e41", "e42", "e51", "e52", "d11", "d12", "d21", "d22", "d31", "d32", "d41", "d42")):
+            w.conv_w[i], w.conv_b[i] = p(bf[name]), p(getattr(self, "unet_" + name).bias.float())
+        for i in range(4):
+            w.up_w[i], w.up_b[i] = p(bf[f"up{i + 1}"]), p(getattr(self, f"unet_upconv{i + 1}").bias.float())
+        w.out_w, w.out_b = p(bf["out"]), p(self.unet_out.bias.float())
+        w.lstm_wx, w.lstm_wh = p(bf["lstm"][0][0]), p(bf["lstm"][0][1])
+        return w, keep
+
+    _stage_ws: dict = {}
+
+    def _unet_stage(self, frames, state, stage, n_traj):
+        """OrigUNet.forward through evfly_unet_forward: one C call enqueues form_input, encoder, ConvLSTM scan, decoder
+        and the output resize on the current stream (same kernels, same order as _unet_bf16)."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        N, _, H, W = frames.shape
+        dev = frames.device
+        h, w = H, W
+        for _ in range(4):
+            h, w = (h - 4) // 2, (w - 4) // 2
+        vh5, vw5 = h - 4, w - 4
+        vh, vw = vh5, vw5
+        for _ in range(4):
+            vh, vw = 2 * vh - 4, 2 * vw - 4
+        need = lib.evfly_unet_workspace_bytes(N, n_traj, H, W)
+        if need <= 0:
+            raise _lib.EvflyError(f"evfly_unet_forward: unsupported shape N={N} n_traj={n_traj} H={H} W={W}")
+        key = (dev, torch.cuda.current_stream().cuda_stream)
+        ws = OrigUNet._stage_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = OrigUNet._stage_ws[key] = torch.empty((need,), dtype=torch.uint8, device=dev)
+        depth = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev)
+        yu = torch.empty((N, 1, vh, vw), dtype=torch.float32, device=dev)
+        hT = torch.empty((n_traj, 512, vh5, vw5), dtype=torch.float32, device=dev)
+        cT = torch.empty_like(hT)
+        h0 = c0 = None
+        if state is not None:
+            h0, c0 = to_dev(state[0][0], dev), to_dev(state[0][1], dev)
+            assert tuple(h0.shape) == tuple(hT.shape) and tuple(c0.shape) == tuple(cT.shape), "ConvLSTM state shape"
+        _lib.check(lib.evfly_unet_forward(C.byref(stage[0]), _lib.ptr(frames), N, n_traj, H, W, float(self.evs_min_cutoff), _lib.ptr(h0), _lib.ptr(c0),
+                                          _lib.ptr(hT), _lib.ptr(cT), _lib.ptr(depth), _lib.ptr(yu), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "evfly_unet_forward")
+        return None, [[hT, cT]], yu, depth
 
     # ---- pieces of the reference API ------------------------------------------------------------
     def form_input(self, x):
@@ -454,12 +516,15 @@ class OrigUNet(PackedModule):
         pk = self.packed()
         im = x[0] = to_dev(x[0], dev)
         N = im.shape[0]
-        if self.num_in_channels == 2 or self.form_BEV > 0:
-            im = self.form_input(im)
         if x[2] is None:
             x[2] = (None, None)
+        use_stage = self.precision == 'bf16' and tc.USE_STAGE_ABI and pk["stage"] is not None and tuple(im.shape[1:]) == (1, self.input_h, self.input_w)
+        if not use_stage and (self.num_in_channels == 2 or self.form_BEV > 0):
+            im = self.form_input(im)
 
-        if self.precision == 'bf16':
+        if use_stage:
+            y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_stage(im, x[2][0], pk["stage"], n_traj)
+        elif self.precision == 'bf16':
             y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_bf16(im, x[2][0], pk["bf16"], n_traj)
         else:
             y_e5_nchw, h_unet, y_upconv, y_interp = self._unet_fp32(im, x[2][0], pk, n_traj)

@@ -394,6 +394,7 @@ def vit_attn(tok, kv, img, bias, heads):
     return out
 
 
+USE_STAGE_ABI = True    # OrigUNet in the shipped configuration through ONE C call (evfly_unet_forward, csrc/stages.cu)
 FUSE_STEM = True     # binary-input stem as a table lookup inside the e12 kernel (form_BEV = 2)
 
 

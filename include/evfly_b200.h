@@ -566,6 +566,51 @@ int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d_stem_w, co
                                 const float* d_bias, void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2,
                                 int Wp2, void* stream);
 
+/* ======================================================================================
+ * STAGE-LEVEL entry points (evfly_b200/csrc/stages.cu): whole stages of the path enqueued from C++ on the caller's
+ * stream -- what the C++ side of evfly_ros (or any host language) binds instead of the per-operator functions
+ * above. Weights arrive packed in caller-owned device memory, intermediates live in a caller-owned workspace,
+ * nothing is allocated and nothing synchronises, so a whole step is capturable in one CUDA graph.
+ * ====================================================================================== */
+
+/* evfly_ros/run.py:334-350 + 250-253: (u8 - 128) * 0.2 (or 0.2 * (n+ - n-) from int32 count frames [N,2,H,W]),
+ * centre crop to h x w, per-frame 97th percentile of |x| (torch.quantile semantics), clip(x / q, -1, 1).
+ * Exactly one of d_u8 [N,H,W] / d_counts is given. d_frames fp32 [N,1,h,w].                                   */
+int evfly_prep_frame(const uint8_t* d_u8, const int32_t* d_counts, int N, int H, int W, int h, int w,
+                     float* d_frames, void* stream);
+
+/* Packed weights of OrigUNet in the shipped configuration (learner/configs/*.txt:39-47: form_BEV = 2,
+ * skip_type = interp, num_recurrent = [1, 0]); layouts as produced by evfly_b200/tc.py:
+ *   e11_w fp32 [32,1,3,3], e11_b fp32 [32]                                            (unet_e11, table lookup)
+ *   conv_w[i] bf16 [Cout][9*Cin] (K index = (kh*3+kw)*Cin + ci), conv_b[i] fp32 [Cout], i = e12, e21, e22, e31,
+ *       e32, e41, e42, e51, e52, d11, d12, d21, d22, d31, d32, d41, d42
+ *   up_w[l] bf16 [4*Cout][Cin] (row = (2a+b)*Cout + co of ConvTranspose2d weight [Cin,Cout,a,b]), up_b[l] fp32 [Cout]
+ *   out_w bf16 [1][32], out_b fp32 [1]                                                                (unet_out)
+ *   lstm_wx / lstm_wh bf16 [2048][512]: the x / h halves of lstm.cell_list.0.conv.weight with rows interleaved
+ *       n = 4*ch + gate (gate order i,f,o,g, convlstm.py:44)                                                  */
+typedef struct evfly_unet_weights {
+    const float* e11_w;
+    const float* e11_b;
+    const void*  conv_w[17];
+    const float* conv_b[17];
+    const void*  up_w[4];
+    const float* up_b[4];
+    const void*  out_w;
+    const float* out_b;
+    const void*  lstm_wx;
+    const void*  lstm_wh;
+} evfly_unet_weights;
+
+/* OrigUNet.forward (learner/learner_models.py:521-585) for N frames = n_traj trajectories x T steps in TIME-MAJOR
+ * order (frame t*n_traj + s; n_traj = 1: the reference's one sequence): form_input (in place on d_frames, like the
+ * reference) -> encoder -> ConvLSTM over T (state in: d_h0 / d_c0 fp32 [n_traj,512,vh,vw] or both NULL; state out:
+ * d_hT / d_cT, each may be NULL) -> decoder -> d_y_upconv fp32 [N,1,.,.] and d_depth fp32 [N,1,H,W] (y_interp).
+ * bf16 tensor-core path. d_ws: evfly_unet_workspace_bytes(N, n_traj, H, W) bytes of scratch.                   */
+int64_t evfly_unet_workspace_bytes(int N, int n_traj, int H, int W);
+int evfly_unet_forward(const evfly_unet_weights* weights, float* d_frames, int N, int n_traj, int H, int W, float cutoff,
+                       const float* d_h0, const float* d_c0, float* d_hT, float* d_cT, float* d_depth,
+                       float* d_y_upconv, void* d_ws, int64_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

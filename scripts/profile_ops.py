@@ -11,6 +11,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "trajectories"
 torch.cuda.set_device(0)
 wl = bench.WORKLOADS[name](0, torch.device("cuda", 0))
 wl.OVERLAP = False      # serial: every entry point timed on its own
+from evfly_b200 import tc
+tc.USE_STAGE_ABI = False   # per-operator calls from Python (the stage-level call enqueues the same kernels from C++)
 for i in range(3):
     wl.step(i)
 torch.cuda.synchronize()

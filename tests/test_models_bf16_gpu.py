@@ -118,3 +118,41 @@ def test_lstmnetvit_bf16_vs_oracle(cuda_lib, manifest):
     s2 = M.mix_transformer_stage(sd, "encoder_blocks.1", s1, **M.STAGE2)
     t2, H2, W2 = m.encoder_blocks[1].encode_bf16(t1, False, 12, H1, W1)
     close_bf16(t2.view(12, H2, W2, 64).permute(0, 3, 1, 2), s2, "stage 2", rel_l2=3e-2, max_scale=0.2)
+
+
+def test_stage_level_abi_equals_per_op_path(cuda_lib, manifest):
+    """evfly_unet_forward (csrc/stages.cu: the whole OrigUNet forward enqueued by one C call) runs the same kernels in the
+    same order as the per-operator Python path: bit-identical outputs and states, fresh and carried, one and several
+    trajectories."""
+    from evfly_b200 import tc
+    m = load("OrigUNet_w_VITFLY_ViTLSTM", manifest, 31, "bf16")
+    n, T = 2, 3
+    frames = synthetic_frames(12, n * T)
+    dv = torch.full((n * T, 1), 4.0)
+
+    def run(stage, state):
+        tc.USE_STAGE_ABI = stage
+        try:
+            hu, hv = state
+            return m.forward_trajectories([frames.clone().cuda(), dv.cuda(), [hu, None], hv], n)
+        finally:
+            tc.USE_STAGE_ABI = True
+    a = run(True, (None, None))
+    b = run(False, (None, None))
+    for k in (0, 1):
+        va, (da, ya, ((hua, _), hva)) = (a, b)[k]
+        if k == 0:
+            first = (va, da, ya, hua, hva)
+    va, da, ya, hua, hva = first
+    vb, (db, yb, ((hub, _), hvb)) = b
+    assert torch.equal(da, db) and torch.equal(ya, yb) and torch.equal(va, vb)
+    assert torch.equal(hua[0][0], hub[0][0]) and torch.equal(hua[0][1], hub[0][1])
+    a2 = run(True, (hua, hva))
+    b2 = run(False, (hub, hvb))
+    assert torch.equal(a2[1][0], b2[1][0]) and torch.equal(a2[0], b2[0])
+    assert torch.equal(a2[1][2][0][0][0][1], b2[1][2][0][0][0][1])
+    # the caller's frames are cut off in place on both paths (learner_models.py:477)
+    fr = frames.clone().cuda()
+    fr[0, 0, 0, 0] = 5e-4
+    m.forward_trajectories([fr, dv.cuda(), [None, None], None], n)
+    assert fr[0, 0, 0, 0].item() == 0.0
