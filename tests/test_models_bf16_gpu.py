@@ -137,14 +137,8 @@ def test_stage_level_abi_equals_per_op_path(cuda_lib, manifest):
             return m.forward_trajectories([frames.clone().cuda(), dv.cuda(), [hu, None], hv], n)
         finally:
             tc.USE_STAGE_ABI = True
-    a = run(True, (None, None))
-    b = run(False, (None, None))
-    for k in (0, 1):
-        va, (da, ya, ((hua, _), hva)) = (a, b)[k]
-        if k == 0:
-            first = (va, da, ya, hua, hva)
-    va, da, ya, hua, hva = first
-    vb, (db, yb, ((hub, _), hvb)) = b
+    va, (da, ya, ((hua, _), hva)) = run(True, (None, None))
+    vb, (db, yb, ((hub, _), hvb)) = run(False, (None, None))
     assert torch.equal(da, db) and torch.equal(ya, yb) and torch.equal(va, vb)
     assert torch.equal(hua[0][0], hub[0][0]) and torch.equal(hua[0][1], hub[0][1])
     a2 = run(True, (hua, hva))
