@@ -116,7 +116,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+DRIVER_SRC = os.path.join(ROOT, "tests", "native", "stage_driver.c")
+DRIVER_BIN = os.path.join(ROOT, "tests", "native", "stage_driver")
+
+
+def _build_driver(nvcc: str, force: bool) -> None:
+    """The plain-C program that drives the stage-level ABI (tests/test_stage_abi_gpu.py)."""
+    if not os.path.exists(DRIVER_SRC):
+        return
+    if not force and os.path.exists(DRIVER_BIN) and os.path.getmtime(DRIVER_BIN) >= max(os.path.getmtime(DRIVER_SRC), os.path.getmtime(HEADER)):
+        return
+    _run([nvcc, "-x", "c", DRIVER_SRC, "-o", DRIVER_BIN, "-L", PKG_DIR, "-l:libevfly_b200.so", "-lcudart",
+          "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../evfly_b200"])
+
+
 def _build_probe(nvcc: str, force: bool) -> None:
+    _build_driver(nvcc, force)
     if not os.path.exists(PROBE_SRC):
         return
     if not force and os.path.exists(PROBE_LIB) and os.path.getmtime(PROBE_LIB) >= os.path.getmtime(PROBE_SRC):

@@ -438,6 +438,8 @@ struct StemE12Args {
 };
 
 constexpr int kStemProducers = 96;      // warps 0, 2, 3
+constexpr int kLutRowB = 80;            // 64 bytes of e11 values + 16 of padding: consecutive patterns start 20 banks apart
+                                        // (unpadded, every lane of a 16-byte table read hit one of two 4-bank groups: 16-way conflicts, ncu r2_stem_e12)
 
 __global__ void __launch_bounds__(384, 1)
 k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const StemE12Args sa) {
@@ -455,7 +457,7 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* s_bias = reinterpret_cast<float*>(w_bar + 2);
     uint8_t* s_ostage = s_halo + Cfg::STAGES * Cfg::HALO_BYTES + 2048;
-    uint8_t* s_lut = s_ostage + Cfg::OUT_STAGE_BYTES;     // [512][32] bf16 = 64 B per pattern
+    uint8_t* s_lut = s_ostage + Cfg::OUT_STAGE_BYTES;     // [512] rows of 32 bf16 (64 B) at a pitch of kLutRowB
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -486,7 +488,7 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
                 a1 += __bfloat162float(__float2bfloat16_rn(sa.stem_w[(c2 + 1) * 9 + k]));
             }
         __nv_bfloat162 v = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
-        reinterpret_cast<__nv_bfloat162*>(s_lut)[i] = v;
+        *reinterpret_cast<__nv_bfloat162*>(s_lut + pt * kLutRowB + (i & 15) * 4) = v;
     }
     tc_fence_before();
     __syncthreads();
@@ -539,17 +541,23 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
             }
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* dst = s_halo + stage * Cfg::HALO_BYTES;
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q0 * 64);
+            {   // chunk order rotated by lane: the four 16-byte reads of a warp instruction spread over all banks
+                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q0 * kLutRowB);
                 const uint32_t sw = (uint32_t)(i0 >> 1) & 3u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + i0 * 64 + ((c ^ sw) << 4)) = src[c];
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint32_t c = (uint32_t)(cc + lane) & 3u;
+                    *reinterpret_cast<uint4*>(dst + i0 * 64 + ((c ^ sw) << 4)) = src[c];
+                }
             }
             if (i1 < Cfg::HALO_ROWS) {
-                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q1 * 64);
+                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q1 * kLutRowB);
                 const uint32_t sw = (uint32_t)(i1 >> 1) & 3u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + i1 * 64 + ((c ^ sw) << 4)) = src[c];
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint32_t c = (uint32_t)(cc + lane) & 3u;
+                    *reinterpret_cast<uint4*>(dst + i1 * 64 + ((c ^ sw) << 4)) = src[c];
+                }
             }
             fence_proxy_async();                                                   // this thread's generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
@@ -757,7 +765,7 @@ extern "C" int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d
     sa.stem_w = d_stem_w;
     sa.stem_b = d_stem_b;
     using Cfg = HaloCfg<32, 32>;
-    constexpr int smem = Cfg::SMEM_BYTES + 512 * 64;
+    constexpr int smem = Cfg::SMEM_BYTES + 512 * kLutRowB;
     CUtensorMap mw;
     const int rc = make_map_w(&mw, d_w, 32, 32);
     if (rc) return rc;
