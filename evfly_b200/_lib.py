@@ -129,7 +129,23 @@ class UNetWeights(C.Structure):
                 ("out_w", _vp), ("out_b", _vp), ("lstm_wx", _vp), ("lstm_wh", _vp)]
 
 
+class VitLayerWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in ("red_w", "red_b", "red_ln_g", "red_ln_b", "kv_w", "kv_b", "attn_img", "attn_bias", "ffn_img", "ffn_bias")]
+
+
+class VitStageWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in ("patch_w", "patch_b", "patch_ln_g", "patch_ln_b")] + [("layer", VitLayerWeights * 2)]
+
+
+class VitLstmWeights(C.Structure):
+    """evfly_vit_lstm_weights (include/evfly_b200.h)."""
+    _fields_ = [("stage", VitStageWeights * 2), ("ds_w", _vp), ("ds_b", _vp), ("dec_w", _vp), ("dec_b", _vp),
+                ("lstm_w_ih", _vp * 3), ("lstm_b", _vp * 3), ("lstm_whh_pairs", _vp * 3), ("lstm_whh_t", _vp * 3), ("fc2_w", _vp), ("fc2_b", _vp)]
+
+
 SIGNATURES.update({
+    "evfly_vit_lstm_workspace_bytes": (_i64, [_i32]),
+    "evfly_vit_lstm_forward": (_i32, [C.POINTER(VitLstmWeights), _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "evfly_prep_frame": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "evfly_unet_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "evfly_unet_forward": (_i32, [C.POINTER(UNetWeights), _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -295,3 +295,179 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
     const int64_t xs[4] = {(int64_t)yvh * yvw, (int64_t)yvh * yvw, yvw, 1}, ys[4] = {(int64_t)H * W, (int64_t)H * W, W, 1};
     return evfly_resize_bilinear_f32(d_y_upconv, xs, d_depth, ys, N, 1, yvh, yvw, H, W, 0, 1.0f, 0.0f, -INFINITY, INFINITY, stream);
 }
+
+// ======================================================================================================================
+// LSTMNetVIT.forward (learner/vitfly_models.py:132-150), bf16 tensor-core path, batches (N >= 8 frames):
+//   depth [N,1,H,W] -> (clamp(2 d, 0, 1) when premap) -> bilinear 60x90 -> two Mix-Transformer stages (fused kernels of
+//   vit_fused.cu) -> PixelShuffle / Upsample / cat -> conv 48->12 -> Linear 4608->512 -> cat[., desvel/10, quat] ->
+//   LSTM(517 -> 128, 3 layers) over time -> Linear 128 -> 3
+// ======================================================================================================================
+namespace evfly {
+
+static int linear_f32(const float* x, int64_t x_ld, int64_t M, int K, const float* w, const float* bias, float* y, int64_t y_ld, int Nout, void* st) {
+    if (M <= 8 && (int64_t)M * K * 4 <= 160 * 1024)
+        return evfly_linear_smallm_f32(x, x_ld, w, bias, nullptr, 0, y, y_ld, (int)M, Nout, K, EVFLY_ACT_NONE, st);
+    evfly_conv2d_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = x;
+    a.w = w;
+    a.bias = bias;
+    a.y = y;
+    a.N = 1;
+    a.Cin = K;
+    a.H = 1;
+    a.W = (int32_t)M;
+    a.Cout = Nout;
+    a.KH = a.KW = 1;
+    a.stride = 1;
+    a.groups = 1;
+    a.xs[1] = 1;
+    a.xs[3] = x_ld;
+    a.ys[1] = 1;
+    a.ys[3] = y_ld;
+    return evfly_conv2d_f32(&a, st);
+}
+
+__global__ void __launch_bounds__(256)
+k_seq_tail(float* __restrict__ seq, const float* __restrict__ desvel, const float* __restrict__ quat, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float* r = seq + (size_t)i * 517 + 512;
+    r[0] = desvel[i] / 10.0f;                                  // X[1] / 10 (vitfly_models.py:144)
+    if (quat) {
+        r[1] = quat[4 * i]; r[2] = quat[4 * i + 1]; r[3] = quat[4 * i + 2]; r[4] = quat[4 * i + 3];
+    } else {                                                   // refine_inputs' default quaternion [1,0,0,0] (:22-25)
+        r[1] = 1.f; r[2] = 0.f; r[3] = 0.f; r[4] = 0.f;
+    }
+}
+
+}  // namespace evfly
+
+extern "C" int64_t evfly_vit_lstm_workspace_bytes(int N) {
+    if (N <= 0) return 0;
+    int64_t t = 4096;
+    auto add = [&](int64_t b) { t += (b + 255) / 256 * 256; };
+    add((int64_t)N * 60 * 90 * 4);                 // resized depth
+    add((int64_t)N * 345 * 32 * 2 * 3);            // stage-1 tokens (ping, pong, attention out)
+    add((int64_t)N * 96 * 64 * 2 * 3);             // stage-2 tokens
+    add((int64_t)N * 6 * 64 * 2);                  // reduced tokens
+    add((int64_t)N * 6 * 128 * 2);                 // kv
+    add((int64_t)N * 16 * 24 * 64 * 2);            // tail cat
+    add((int64_t)N * 16 * 24 * 32 * 2);            // tail conv out
+    add((int64_t)N * 517 * 4);                     // seq
+    add((int64_t)N * 512 * 4);                     // gate pre-activations
+    add((int64_t)N * 128 * 4 * 2);                 // layer outputs (ping, pong)
+    return t;
+}
+
+extern "C" int evfly_vit_lstm_forward(const evfly_vit_lstm_weights* w, const float* d_depth, int N, int n_traj, int H, int W, int premap_clamp,
+                                      const float* d_desvel, const float* d_quat, const float* d_h0, const float* d_c0, float* d_hT, float* d_cT,
+                                      float* d_vel, void* d_ws, int64_t ws_bytes, void* stream) {
+    EVFLY_REQUIRE(w && d_depth && d_desvel && d_vel && d_hT && d_cT && d_ws && N >= 8 && n_traj > 0 && N % n_traj == 0,
+                  "vit_lstm_forward: bad argument (batches of N >= 8 frames; smaller batches go through the per-operator entry points)");
+    EVFLY_REQUIRE((d_h0 == nullptr) == (d_c0 == nullptr), "vit_lstm_forward: h0 / c0 go together");
+    const int64_t need = evfly_vit_lstm_workspace_bytes(N);
+    if (ws_bytes < need) {
+        set_error("vit_lstm_forward: workspace of %lld bytes, %lld needed", (long long)ws_bytes, (long long)need);
+        return EVFLY_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Bump ws{reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~(uintptr_t)255), ws_bytes - 256};
+    // ---- refine_inputs (:28-29) fused with the wrapper's clamp (learner_models.py:634)
+    const float* depth60 = d_depth;
+    if (H != 60 || W != 90 || premap_clamp) {
+        float* r = (float*)ws.take((int64_t)N * 60 * 90 * 4);
+        const int64_t xs[4] = {(int64_t)H * W, (int64_t)H * W, W, 1}, ys[4] = {60 * 90, 60 * 90, 90, 1};
+        if (premap_clamp) RC(evfly_resize_bilinear_premap_f32(d_depth, xs, r, ys, N, 1, H, W, 60, 90, 0, 2.0f, 0.0f, 1.0f, stream));
+        else RC(evfly_resize_bilinear_f32(d_depth, xs, r, ys, N, 1, H, W, 60, 90, 0, 1.0f, 0.0f, -INFINITY, INFINITY, stream));
+        depth60 = r;
+    }
+    // ---- the two Mix-Transformer stages (ViTsubmodules.py:122-148)
+    const void* stage_in = depth60;
+    void* tok_out[2] = {nullptr, nullptr};
+    const int TH[2] = {15, 8}, TW[2] = {23, 12}, TC[2] = {32, 64}, CIN[2] = {1, 32}, KP[2] = {7, 3}, SP[2] = {4, 2}, PP[2] = {3, 1}, RR[2] = {8, 4},
+              HEADS[2] = {1, 2}, IH[2] = {60, 15}, IW[2] = {90, 23};
+    for (int s = 0; s < 2; ++s) {
+        const evfly_vit_stage_weights& sw = w->stage[s];
+        const int C = TC[s], Ntok = TH[s] * TW[s];
+        const int64_t tok_bytes = (int64_t)N * Ntok * C * 2;
+        void* a = ws.take(tok_bytes);
+        void* b = ws.take(tok_bytes);
+        void* c = ws.take(tok_bytes);
+        const int h2 = (TH[s] - RR[s]) / RR[s] + 1, w2 = (TW[s] - RR[s]) / RR[s] + 1, n_kv = h2 * w2;
+        void* red = ws.take((int64_t)N * n_kv * C * 2);
+        void* kv = ws.take((int64_t)N * n_kv * 2 * C * 2);
+        EVFLY_REQUIRE(ws.ok, "vit_lstm_forward: workspace exhausted (internal sizing error)");
+        RC(evfly_patch_embed_ln_bf16(stage_in, s == 0, sw.patch_w, sw.patch_b, sw.patch_ln_g, sw.patch_ln_b, a, N, IH[s], IW[s], CIN[s], C, KP[s], SP[s], PP[s],
+                                     1e-5f, stream));
+        void* cur = a;
+        void* spare = b;
+        for (int l = 0; l < 2; ++l) {
+            const evfly_vit_layer_weights& lw = sw.layer[l];
+            // spatial-reduction attention: k = s = r conv + LayerNorm, K/V projection, fused q / softmax / final projection + residual
+            RC(evfly_patch_embed_ln_bf16(cur, 0, lw.red_w, lw.red_b, lw.red_ln_g, lw.red_ln_b, red, N, TH[s], TW[s], C, C, RR[s], RR[s], 0, 1e-5f, stream));
+            evfly_tc_conv_args g;
+            memset(&g, 0, sizeof(g));
+            g.x = red;
+            g.w = lw.kv_w;
+            g.bias = lw.kv_b;
+            g.out = kv;
+            g.M_rows = (int64_t)N * n_kv;
+            g.out_ld = 2 * C;
+            g.Cin = C;
+            g.n_rows = 2 * C;
+            g.taps = 1;
+            RC(evfly_tc_conv_bf16(&g, stream));
+            RC(evfly_vit_attn_bf16(cur, kv, lw.attn_img, lw.attn_bias, c, N, Ntok, C, HEADS[s], n_kv, stream));
+            // MixFFN + residual + LayerNorm in one launch
+            RC(evfly_vit_ffn_bf16(c, lw.ffn_img, lw.ffn_bias, spare, N, TH[s], TW[s], C, 1e-5f, stream));
+            void* t = cur;
+            cur = spare;
+            spare = t;
+        }
+        tok_out[s] = cur;
+        stage_in = cur;
+    }
+    // ---- tail (vitfly_models.py:136-143): cat[PixelShuffle(2)(s2), Upsample(16x24, align_corners)(s1)] -> conv 48->12 -> decoder Linear
+    void* cat = ws.take((int64_t)N * 16 * 24 * 64 * 2);
+    void* feat = ws.take((int64_t)N * 16 * 24 * 32 * 2);
+    float* seq = (float*)ws.take((int64_t)N * 517 * 4);
+    float* gx = (float*)ws.take((int64_t)N * 512 * 4);
+    float* hs0 = (float*)ws.take((int64_t)N * 128 * 4);
+    float* hs1 = (float*)ws.take((int64_t)N * 128 * 4);
+    EVFLY_REQUIRE(ws.ok, "vit_lstm_forward: workspace exhausted (internal sizing error)");
+    RC(evfly_shuffle_upsample_cat_bf16(tok_out[1], 8, 12, 64, tok_out[0], 15, 23, 32, cat, N, 64, stream));
+    RC(evfly_tc_conv3x3_same_bf16(cat, w->ds_w, w->ds_b, feat, N, 16, 24, 64, 32, 0, stream));
+    {
+        evfly_tc_conv_args g;
+        memset(&g, 0, sizeof(g));
+        g.x = feat;
+        g.w = w->dec_w;
+        g.bias = w->dec_b;
+        g.out_f32 = seq;
+        g.M_rows = N;
+        g.out_ld = 517;
+        g.Cin = 16 * 24 * 32;
+        g.n_rows = 512;
+        g.taps = 1;
+        RC(evfly_tc_conv_bf16(&g, stream));
+    }
+    k_seq_tail<<<(N + 255) / 256, 256, 0, st>>>(seq, d_desvel, d_quat, N);
+    EVFLY_LAUNCHED();
+    // ---- LSTM over time (:146), n_traj sequences side by side, then the velocity head (:149)
+    const int T = N / n_traj;
+    const float* inp = seq;
+    int in_ld = 517, in_k = 517;
+    float* outs[2] = {hs0, hs1};
+    for (int l = 0; l < 3; ++l) {
+        RC(linear_f32(inp, in_ld, N, in_k, w->lstm_w_ih[l], w->lstm_b[l], gx, 512, 512, stream));
+        float* hs = outs[l & 1];
+        const float* h0 = d_h0 ? d_h0 + (size_t)l * n_traj * 128 : nullptr;
+        const float* c0 = d_c0 ? d_c0 + (size_t)l * n_traj * 128 : nullptr;
+        if (T >= 16) RC(evfly_lstm_seq_smemw(gx, w->lstm_whh_pairs[l], h0, c0, hs, d_hT + (size_t)l * n_traj * 128, d_cT + (size_t)l * n_traj * 128, T, 128, n_traj, stream));
+        else RC(evfly_lstm_seq_f32(gx, w->lstm_whh_t[l], h0, c0, hs, d_hT + (size_t)l * n_traj * 128, d_cT + (size_t)l * n_traj * 128, T, 128, n_traj, stream));
+        inp = hs;
+        in_ld = in_k = 128;
+    }
+    return linear_f32(inp, 128, N, 128, w->fc2_w, w->fc2_b, d_vel, 3, 3, stream);
+}

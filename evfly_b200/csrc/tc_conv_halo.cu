@@ -527,17 +527,19 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
         }
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const unsigned q0 = qa[0], q1 = qb[0];
+        // unrolled by kDepth so that slot d of the lookahead is a FIXED register: rotating the values through moves would
+        // make the first move wait for a load issued one tile ago (the scoreboard tracks registers, not values)
+#pragma unroll 1
+        for (long long base = blockIdx.x; base < total_tiles; base += (long long)kDepth * gridDim.x) {
 #pragma unroll
-            for (int d = 0; d + 1 < kDepth; ++d) {
-                qa[d] = qa[d + 1];
-                qb[d] = qb[d + 1];
-            }
-            qa[kDepth - 1] = qb[kDepth - 1] = 0;
+          for (int d = 0; d < kDepth; ++d) {
+            const long long tile = base + (long long)d * gridDim.x;
+            if (tile >= total_tiles) break;
+            const unsigned q0 = qa[d], q1 = qb[d];
+            qa[d] = qb[d] = 0;
             {
-                const long long tl = (long long)tile + (long long)kDepth * gridDim.x;
-                if (tl < total_tiles) fetch((int)tl, qa[kDepth - 1], qb[kDepth - 1]);
+                const long long tl = tile + (long long)kDepth * gridDim.x;
+                if (tl < total_tiles) fetch((int)tl, qa[d], qb[d]);
             }
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* dst = s_halo + stage * Cfg::HALO_BYTES;
@@ -563,6 +565,7 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[stage]);                          // the stage is full when the three producer warps have arrived
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (as k_tc_conv3x3_halo) =================

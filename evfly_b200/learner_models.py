@@ -564,6 +564,12 @@ class OrigUNet_w_VITFLY_ViTLSTM(nn.Module):
         x = X[0]
         _, (x_depth, y_upconv, (h_unet, h_velpred)) = self.origunet.forward([x, None, X[2]], n_traj=n_traj)
         # * 2 roughly matches the depth scale VITFLY_ViTLSTM was trained on (:634)
+        v = self.vitfly_vitlstm
+        if v._stage_usable(x_depth.shape[0]):
+            # clamp + resize + both ViT stages + LSTM + head enqueued by one C call (evfly_vit_lstm_forward)
+            v._check_inference()
+            x_vel, h_vitlstm = v.forward_from_depth(x_depth, X[1], None, X[3], n_traj=n_traj, premap_clamp=True)
+            return x_vel, (x_depth, y_upconv, ((h_unet, h_velpred), h_vitlstm))
         if tuple(x_depth.shape[-2:]) != (60, 90):
             # vitfly's refine_inputs (vitfly_models.py:28-29) would resize the clamped depth to 60x90 next: do both in
             # one pass over the four samples of each output pixel instead of materialising the full-size clamped image

@@ -127,7 +127,74 @@ class LSTMNetVIT(_ViTEncoder):
 
     def _pack(self):
         dec = sn_effective_weight(self.decoder)
-        return {"decoder": dec, "tail": self._pack_tail_tc(dec), "fc2": sn_effective_weight(self.nn_fc2), "lstm": pack_lstm(self.lstm)}
+        pk = {"decoder": dec, "tail": self._pack_tail_tc(dec), "fc2": sn_effective_weight(self.nn_fc2), "lstm": pack_lstm(self.lstm)}
+        pk["stage"] = self._pack_stage(pk) if dec.is_cuda else None
+        return pk
+
+    # ---- stage-level C ABI (csrc/stages.cu evfly_vit_lstm_forward): the whole forward enqueued by ONE call ----------
+    def _pack_stage(self, pk):
+        from . import _lib
+        w = _lib.VitLstmWeights()
+        keep = []
+
+        def p(t):
+            t = t.contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        for s, blk in enumerate(self.encoder_blocks):
+            bpk = blk.packed()
+            c, ln = blk.patchMerge.cn1, blk.patchMerge.layerNorm
+            st = w.stage[s]
+            st.patch_w, st.patch_b, st.patch_ln_g, st.patch_ln_b = p(bpk["patch_w"]), p(c.bias.float()), p(ln.weight.float()), p(ln.bias.float())
+            for l, (attn, lw) in enumerate(zip(blk._attn, bpk["layers"])):
+                if lw["attn_fused"] is None or lw["ffn_fused"] is None:
+                    return None
+                L = st.layer[l]
+                L.red_w, L.red_b, L.red_ln_g, L.red_ln_b = p(lw["red_w"]), p(attn.cn1.bias.float()), p(attn.ln1.weight.float()), p(attn.ln1.bias.float())
+                L.kv_w, L.kv_b = p(lw["kv"]), p(attn.keyValueExtractor.bias.float())
+                L.attn_img, L.attn_bias = p(lw["attn_fused"][0]), p(lw["attn_fused"][1])
+                L.ffn_img, L.ffn_bias = p(lw["ffn_fused"][0]), p(lw["ffn_fused"][1])
+        w.ds_w, w.ds_b = p(pk["tail"]["ds_w"]), p(pk["tail"]["ds_b"])
+        w.dec_w, w.dec_b = p(pk["tail"]["dec"]), p(self.decoder.bias.float())
+        for l, (w_ih, b, w_hh_t, pairs, _w_hh) in enumerate(pk["lstm"]):
+            if pairs is None or b is None:
+                return None
+            w.lstm_w_ih[l], w.lstm_b[l], w.lstm_whh_pairs[l], w.lstm_whh_t[l] = p(w_ih), p(b), p(pairs), p(w_hh_t)
+        w.fc2_w, w.fc2_b = p(pk["fc2"]), p(self.nn_fc2.bias.float())
+        return w, keep
+
+    _stage_ws: dict = {}
+
+    def forward_from_depth(self, depth, desvel, quat, state, n_traj=1, premap_clamp=False):
+        """evfly_vit_lstm_forward: depth [N,1,H,W] (any size; premap_clamp: clamp(2 d, 0, 1) first, learner_models.py:634)
+        -> (vel [N,3], (h, c)). Batches of N >= 8 frames on the bf16 path."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        stage = self.packed()["stage"]
+        N, _, H, W = depth.shape
+        dev = depth.device
+        need = lib.evfly_vit_lstm_workspace_bytes(N)
+        key = (dev, torch.cuda.current_stream().cuda_stream)
+        ws = LSTMNetVIT._stage_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = LSTMNetVIT._stage_ws[key] = torch.empty((need,), dtype=torch.uint8, device=dev)
+        st_shape = (3, 128) if n_traj == 1 else (3, n_traj, 128)
+        hT = torch.empty(st_shape, dtype=torch.float32, device=dev)
+        cT = torch.empty(st_shape, dtype=torch.float32, device=dev)
+        h0 = c0 = None
+        if state is not None:
+            h0, c0 = to_dev(state[0], dev), to_dev(state[1], dev)
+            assert tuple(h0.shape) == st_shape and tuple(c0.shape) == st_shape, "LSTM state shape"
+        vel = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        dv = to_dev(desvel, dev).reshape(N)
+        _lib.check(lib.evfly_vit_lstm_forward(C.byref(stage[0]), _lib.ptr(depth), N, n_traj, H, W, int(premap_clamp), _lib.ptr(dv),
+                                              None if quat is None else _lib.ptr(to_dev(quat, dev)), _lib.ptr(h0), _lib.ptr(c0), _lib.ptr(hT), _lib.ptr(cT),
+                                              _lib.ptr(vel), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "evfly_vit_lstm_forward")
+        return vel, (hT, cT)
+
+    def _stage_usable(self, N):
+        return self.precision == 'bf16' and tc.USE_STAGE_ABI and N >= 16 and self.packed()["stage"] is not None
 
     def forward_trajectories(self, X, n_traj):
         """Extension: n_traj sequences advance together (rows time-major, state [3, n_traj, 128])."""
@@ -137,6 +204,8 @@ class LSTMNetVIT(_ViTEncoder):
         X = _inputs(self, X)
         pk = self.packed()
         N = X[0].shape[0]
+        if self._stage_usable(N):
+            return self.forward_from_depth(X[0], X[1], X[2], X[3] if len(X) > 3 else None, n_traj)
         seq, feat_out = _meta_concat(512, [(X[1], 1.0, 10.0), (X[2], 1.0, 1.0)], N, X[0].device)   # X[1]/10
         if self.precision == 'bf16' and N >= 16:
             # batches: tail + decoder Linear on the tensor cores, fp32 out into the concat buffer

@@ -611,6 +611,41 @@ int evfly_unet_forward(const evfly_unet_weights* weights, float* d_frames, int N
                        const float* d_h0, const float* d_c0, float* d_hT, float* d_cT, float* d_depth,
                        float* d_y_upconv, void* d_ws, int64_t ws_bytes, void* stream);
 
+/* Packed weights of LSTMNetVIT (learner/vitfly_models.py:111-150), layouts of evfly_b200/tc.py and _modbase.py:
+ *   per stage: patch_w fp32 [k*k*Cin][C] (K index (kh*k+kw)*Cin + ci), patch_b, LayerNorm gamma / beta fp32 [C]
+ *   per layer: red_w fp32 [r*r*C][C], red_b, ln1 gamma / beta; kv_w bf16 [2C][C], kv_b fp32 [2C];
+ *              attn_img / attn_bias (tc.pack_vit_attn), ffn_img / ffn_bias (tc.pack_vit_ffn)
+ *   ds_w bf16 [32][9*64] / ds_b fp32 [32] (down_sample 48 -> 12 zero-padded), dec_w bf16 [512][16*24*32] (decoder Linear with
+ *   spectral norm folded, re-indexed to NHWC), dec_b fp32 [512]
+ *   LSTM layer l: w_ih fp32 [512][in], b fp32 [512] (b_ih + b_hh), whh_pairs bf16x2 [64][512], whh_t fp32 [128][512]
+ *   fc2_w fp32 [3][128] (spectral norm folded), fc2_b fp32 [3]                                                     */
+typedef struct evfly_vit_layer_weights {
+    const float* red_w; const float* red_b; const float* red_ln_g; const float* red_ln_b;
+    const void*  kv_w;  const float* kv_b;
+    const void*  attn_img; const float* attn_bias;
+    const void*  ffn_img;  const float* ffn_bias;
+} evfly_vit_layer_weights;
+typedef struct evfly_vit_stage_weights {
+    const float* patch_w; const float* patch_b; const float* patch_ln_g; const float* patch_ln_b;
+    evfly_vit_layer_weights layer[2];
+} evfly_vit_stage_weights;
+typedef struct evfly_vit_lstm_weights {
+    evfly_vit_stage_weights stage[2];
+    const void*  ds_w;  const float* ds_b;
+    const void*  dec_w; const float* dec_b;
+    const float* lstm_w_ih[3]; const float* lstm_b[3]; const void* lstm_whh_pairs[3]; const float* lstm_whh_t[3];
+    const float* fc2_w; const float* fc2_b;
+} evfly_vit_lstm_weights;
+
+/* LSTMNetVIT.forward for N >= 8 frames = n_traj sequences x T steps, time-major: d_depth fp32 [N,1,H,W] (premap_clamp:
+ * clamp(2 d, 0, 1) first -- learner_models.py:634), d_desvel fp32 [N], d_quat fp32 [N,4] or NULL ([1,0,0,0]);
+ * LSTM state in d_h0 / d_c0 fp32 [3,n_traj,128] or both NULL, out d_hT / d_cT; d_vel fp32 [N,3].                      */
+int64_t evfly_vit_lstm_workspace_bytes(int N);
+int evfly_vit_lstm_forward(const evfly_vit_lstm_weights* weights, const float* d_depth, int N, int n_traj, int H, int W,
+                           int premap_clamp, const float* d_desvel, const float* d_quat, const float* d_h0,
+                           const float* d_c0, float* d_hT, float* d_cT, float* d_vel, void* d_ws, int64_t ws_bytes,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,3 +150,27 @@ def test_stage_level_abi_equals_per_op_path(cuda_lib, manifest):
     fr[0, 0, 0, 0] = 5e-4
     m.forward_trajectories([fr, dv.cuda(), [None, None], None], n)
     assert fr[0, 0, 0, 0].item() == 0.0
+
+
+def test_vit_lstm_stage_abi_equals_per_op_path(cuda_lib, manifest):
+    """evfly_vit_lstm_forward (clamp + resize + both ViT stages + LSTM + head in one C call) against the per-operator Python
+    path on the same kernels: 2 trajectories x 16 steps, fresh and carried state."""
+    from evfly_b200 import tc
+    from oracle.synth_ckpt import synthetic_depth
+    m = load("LSTMNetVIT", manifest, 11, "bf16")
+    n, T = 2, 16
+    depth = torch.nn.functional.interpolate(synthetic_depth(4, n * T), size=(260, 346), mode="bilinear").cuda()
+    dv = torch.full((n * T, 1), 4.0, device="cuda")
+
+    def run(stage, state):
+        tc.USE_STAGE_ABI = stage
+        try:
+            return m.forward_trajectories([depth.clone(), dv, None, state], n)
+        finally:
+            tc.USE_STAGE_ABI = True
+    va, (ha, ca) = run(True, None)
+    vb, (hb, cb) = run(False, None)
+    assert torch.equal(va, vb) and torch.equal(ha, hb) and torch.equal(ca, cb)
+    va2, _ = run(True, (ha, ca))
+    vb2, _ = run(False, (hb, cb))
+    assert torch.equal(va2, vb2)
