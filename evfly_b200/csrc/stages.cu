@@ -350,8 +350,10 @@ extern "C" int64_t evfly_vit_lstm_workspace_bytes(int N) {
     add((int64_t)N * 60 * 90 * 4);                 // resized depth
     add((int64_t)N * 345 * 32 * 2 * 3);            // stage-1 tokens (ping, pong, attention out)
     add((int64_t)N * 96 * 64 * 2 * 3);             // stage-2 tokens
-    add((int64_t)N * 6 * 64 * 2);                  // reduced tokens
-    add((int64_t)N * 6 * 128 * 2);                 // kv
+    for (int s = 0; s < 2; ++s) {                  // per stage: reduced tokens and their K/V projection
+        add((int64_t)N * 6 * 64 * 2);
+        add((int64_t)N * 6 * 128 * 2);
+    }
     add((int64_t)N * 16 * 24 * 64 * 2);            // tail cat
     add((int64_t)N * 16 * 24 * 32 * 2);            // tail conv out
     add((int64_t)N * 517 * 4);                     // seq

@@ -65,6 +65,17 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// explicit shared-space 16-byte accesses: through generic pointers the table copy compiled to LD.E / ST.E, whose stores
+// were the producers' top stall (ncu source page, profiles/r2_ncu_stem_e12.txt)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // Epilogue shared by the two halo kernels: warps 4-7 take the even local tiles, warps 8-11 the odd ones.
 template <int COUT, int NACC, bool STAGE_OUT>
 __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int lane, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -76,7 +87,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
     const int r = row >> 3, c = row & 7;
     constexpr bool kStage = STAGE_OUT;
     constexpr int kCP = COUT / 8;            // 16-byte chunks per pixel
-    uint8_t* my_stage = s_ostage + (warp - 4) * (32 * COUT * 2);
+    const uint32_t my_stage = smem_u32(s_ostage) + (warp - 4) * (32 * COUT * 2);      // shared-space address: STS / LDS, not generic ST / LD
     constexpr bool kBiasRegs = COUT <= 64;   // bias in registers (same for every tile); from shared memory for wide outputs
     float breg[kBiasRegs ? COUT : 1];
     if constexpr (kBiasRegs) {
@@ -115,7 +126,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                 }
                 if constexpr (kStage) {
                     // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
-                    *reinterpret_cast<uint4*>(my_stage + lane * (COUT * 2) + ((((c0 >> 3) + q) ^ (kCP == 4 ? ((lane >> 1) & 3) : (lane & 7))) << 4)) = pack8_bf16(f);
+                    sts128(my_stage + lane * (COUT * 2) + ((((c0 >> 3) + q) ^ (kCP == 4 ? ((lane >> 1) & 3) : (lane & 7))) << 4), pack8_bf16(f));
                 } else {
                     if (ok) reinterpret_cast<uint4*>(o + c0)[q] = pack8_bf16(f);
                 }
@@ -138,7 +149,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                 const int id = j * 32 + lane, px = id / kCP, ch = id % kCP;
                 const int poh = ty * 16 + ew * 4 + (px >> 3), pow_ = tx * 8 + (px & 7);
                 if (poh < p.out_vh && pow_ < p.out_vw) {
-                    const uint4 val = *reinterpret_cast<const uint4*>(my_stage + px * (COUT * 2) + ((ch ^ (kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4));
+                    const uint4 val = lds128(my_stage + px * (COUT * 2) + ((ch ^ (kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4));
                     *reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + poh) * p.Wp + pow_) * COUT + ch * 8) = val;
                 }
             }
@@ -503,6 +514,7 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
             for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * Cfg::W_TAP_BYTES, &map_w, w_bar, t * 32, 0);
         }
         const int EH = p.Hp - 2, EW = p.Wp - 2;
+        const uint32_t halo_u32 = smem_u32(s_halo), lut_u32 = smem_u32(s_lut);
         // halo pixels of this thread: idx = pt_id and pt_id + 96 (180 per tile)
         const int i0 = pt_id, i1 = pt_id + kStemProducers;
         const int hy0 = i0 / 10, hx0 = i0 - hy0 * 10, hy1 = i1 / 10, hx1 = i1 - hy1 * 10;
@@ -542,24 +554,24 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
                 if (tl < total_tiles) fetch((int)tl, qa[d], qb[d]);
             }
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* dst = s_halo + stage * Cfg::HALO_BYTES;
+            const uint32_t dst = halo_u32 + stage * Cfg::HALO_BYTES;
             {   // chunk order rotated by lane: the four 16-byte reads of a warp instruction spread over all banks
-                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q0 * kLutRowB);
+                const uint32_t src = lut_u32 + q0 * kLutRowB;
                 const uint32_t sw = (uint32_t)(i0 >> 1) & 3u;
+                uint4 v[4];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const uint32_t c = (uint32_t)(cc + lane) & 3u;
-                    *reinterpret_cast<uint4*>(dst + i0 * 64 + ((c ^ sw) << 4)) = src[c];
-                }
+                for (int cc = 0; cc < 4; ++cc) v[cc] = lds128(src + ((((uint32_t)(cc + lane)) & 3u) << 4));
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) sts128(dst + i0 * 64 + (((((uint32_t)(cc + lane)) & 3u) ^ sw) << 4), v[cc]);
             }
             if (i1 < Cfg::HALO_ROWS) {
-                const uint4* src = reinterpret_cast<const uint4*>(s_lut + q1 * kLutRowB);
+                const uint32_t src = lut_u32 + q1 * kLutRowB;
                 const uint32_t sw = (uint32_t)(i1 >> 1) & 3u;
+                uint4 v[4];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const uint32_t c = (uint32_t)(cc + lane) & 3u;
-                    *reinterpret_cast<uint4*>(dst + i1 * 64 + ((c ^ sw) << 4)) = src[c];
-                }
+                for (int cc = 0; cc < 4; ++cc) v[cc] = lds128(src + ((((uint32_t)(cc + lane)) & 3u) << 4));
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) sts128(dst + i1 * 64 + (((((uint32_t)(cc + lane)) & 3u) ^ sw) << 4), v[cc]);
             }
             fence_proxy_async();                                                   // this thread's generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
