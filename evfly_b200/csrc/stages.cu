@@ -176,7 +176,6 @@ extern "C" int64_t evfly_unet_workspace_bytes(int N, int n_traj, int H, int W) {
     if (!g.ok || N <= 0 || n_traj <= 0 || N % n_traj) return 0;
     int64_t total = 4096;
     auto add = [&](int64_t b) { total += (b + 255) / 256 * 256; };
-    add((int64_t)N * H * W * 4);                      // mask
     add((int64_t)N * (H - 2) * (W - 2) * 2);          // stem patterns
     for (int l = 0; l < 5; ++l) {
         const int64_t px = (int64_t)N * g.Hp[l] * g.Wp[l];
@@ -219,14 +218,12 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
     Bump ws{reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~(uintptr_t)255), ws_bytes - 256};
     const int T = N / n_traj;
 
-    // ---- form_input (learner_models.py:476-494, form_BEV = 2): in place on the caller's frames, mask out
-    float* mask = (float*)ws.take((int64_t)N * H * W * 4);
-    RC(evfly_form_input_f32(d_frames, mask, (int64_t)N * H * W, (int64_t)H * W, 2, cutoff, stream));
-    // ---- encoder (learner_models.py:533-541)
+    // ---- form_input (learner_models.py:476-494, form_BEV = 2: cutoff in place on the caller's frames, 0/1 mask) fused with the
+    //      extraction of the stem's 3x3 mask patterns; ---- encoder (learner_models.py:533-541)
     void* ye[5];
     {
         uint16_t* pat = (uint16_t*)ws.take((int64_t)N * (H - 2) * (W - 2) * 2);
-        RC(evfly_stem_patterns(mask, pat, N, H, W, stream));
+        RC(evfly_form_patterns(d_frames, cutoff, pat, N, H, W, stream));
         ye[0] = ws.take((int64_t)N * H * W * 32 * 2);
         void* pooled = ws.take((int64_t)N * g.Hp[1] * g.Wp[1] * 32 * 2);
         RC(evfly_tc_stem_e12_pool_bf16(pat, wts->e11_w, wts->e11_b, wts->conv_w[0], wts->conv_b[0], ye[0], pooled, N, H, W, 1, g.Hp[1], g.Wp[1], stream));
@@ -267,6 +264,7 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
     }
     // ---- decoder (learner_models.py:553-585): bilinear skip || ConvTranspose2d(2,2) -> cat -> two 3x3 convs
     const void* y = h_all + P * Ch;       // h_1 .. h_T = the ConvLSTM output sequence, frame t*n_traj + s
+    float* out32 = nullptr;
     int yHp = Hp5, yWp = Wp5, yvh = vh5, yvw = vw5;
     for (int lvl = 1; lvl <= 4; ++lvl) {
         const int C = kEncC[5 - lvl], Cin = kEncC[6 - lvl];
@@ -280,7 +278,13 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
         RC(evfly_resize_bilinear_nhwc_bf16(ye[el], cat, N, g.Hp[el], g.Wp[el], g.ev[el][0], g.ev[el][1], C, oh, ow, 2 * C, 0, stream));
         RC(convt2x2(y, N, yHp, yWp, yvh, yvw, Cin, wts->up_w[lvl - 1], wts->up_b[lvl - 1], C, cat, 2 * C, C, stream));
         RC(conv3(cat, N, oh, ow, oh, ow, 2 * C, wts->conv_w[9 + 2 * (lvl - 1)], wts->conv_b[9 + 2 * (lvl - 1)], C, d1, nullptr, 0, 0, stream));
-        RC(conv3(d1, N, oh, ow, oh - 2, ow - 2, C, wts->conv_w[10 + 2 * (lvl - 1)], wts->conv_b[10 + 2 * (lvl - 1)], C, d2, nullptr, 0, 0, stream));
+        if (lvl == 4) {
+            // unet_d42 with unet_out (1x1 to one channel, :583) in its epilogue: the 32-channel activation is never written
+            out32 = (float*)d2;       // N*oh*ow fp32 fit the N*oh*ow*32 bf16 reserved for d42's output
+            RC(evfly_tc_conv3x3_halo_out1_bf16(d1, wts->conv_w[16], wts->conv_b[16], wts->out_w, wts->out_b, out32, N, oh, ow, oh - 2, ow - 2, C, C, 1, stream));
+        } else {
+            RC(conv3(d1, N, oh, ow, oh - 2, ow - 2, C, wts->conv_w[10 + 2 * (lvl - 1)], wts->conv_b[10 + 2 * (lvl - 1)], C, d2, nullptr, 0, 0, stream));
+        }
         y = d2;
         yHp = oh;
         yWp = ow;
@@ -288,9 +292,6 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
         yvw = ow - 4;
     }
     // ---- 1x1 output conv (:583) and the bilinear resize back to the input size (:497)
-    float* out32 = (float*)ws.take((int64_t)N * yHp * yWp * 4);
-    EVFLY_REQUIRE(ws.ok, "unet_forward: workspace exhausted (internal sizing error)");
-    RC(gemm_f32out(y, (int64_t)N * yHp * yWp, 32, wts->out_w, wts->out_b, 1, out32, stream));
     RC(evfly_nhwc_to_nchw_f32(out32, 1, d_y_upconv, N, 1, yvh, yvw, yHp, yWp, stream));
     const int64_t xs[4] = {(int64_t)yvh * yvw, (int64_t)yvh * yvw, yvw, 1}, ys[4] = {(int64_t)H * W, (int64_t)H * W, W, 1};
     return evfly_resize_bilinear_f32(d_y_upconv, xs, d_depth, ys, N, 1, yvh, yvw, H, W, 0, 1.0f, 0.0f, -INFINITY, INFINITY, stream);

@@ -28,6 +28,12 @@ struct HaloArgs {
     int N, Hp, Wp, out_vh, out_vw;
     int tiles_x, tiles_y;
     int relu;
+    // optional fused 1x1 output conv to ONE channel (unet_out after unet_d42, learner_models.py:583): out1[n, oh, ow] =
+    // b1 + sum_c bf16(act(conv)[c]) * w1[c] in fp32 on the same pitch grid; with it `out` may be null (the COUT-channel
+    // activation is then never written)
+    const float* w1;      // [COUT] (bf16-rounded values as fp32), or nullptr
+    const float* b1;      // [1]
+    float* out1;          // [N, Hp, Wp] fp32
 };
 
 template <int CIN, int COUT>
@@ -111,6 +117,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
         __nv_bfloat16* po = p.pool_out ? p.pool_out + (((long long)n * p.Hp2 + (oh >> 1)) * p.Wp2 + (ow >> 1)) * COUT : nullptr;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        float dot1 = 0.f;
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 32) {
             uint32_t v[32];
@@ -124,6 +131,11 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                     const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
                     f[e] = p.relu ? fmaxf(x, 0.f) : x;
                 }
+                if (p.w1) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dot1 = fmaf(__bfloat162float(__float2bfloat16_rn(f[e])), __ldg(p.w1 + c0 + q * 8 + e), dot1);
+                }
+                if (!p.out) continue;
                 if constexpr (kStage) {
                     // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
                     sts128(my_stage + lane * (COUT * 2) + ((((c0 >> 3) + q) ^ (kCP == 4 ? ((lane >> 1) & 3) : (lane & 7))) << 4), pack8_bf16(f));
@@ -140,7 +152,8 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                 }
             }
         }
-        if constexpr (kStage) {
+        if (p.w1 && ok) p.out1[((long long)n * p.Hp + oh) * p.Wp + ow] = dot1 + __ldg(p.b1);
+        if constexpr (kStage) if (p.out) {
             // write-out: instruction j stores chunks [32j, 32j+32) of the warp's 32 pixels = 512 contiguous bytes
             // (8 pixels of one output row are adjacent in the NHWC grid)
             __syncwarp();
@@ -442,6 +455,46 @@ k_stem_patterns(const float* __restrict__ mask, uint16_t* __restrict__ pat, int 
     }
 }
 
+// form_input (learner_models.py:476-491, form_BEV = 2) and the pattern extraction in ONE pass over the frame: values below the
+// cutoff are zeroed IN PLACE (the reference mutates the caller's tensor, :477) and the 0/1 mask exists only as the 9 bits
+// under each e11 pixel. One thread per 8 consecutive e11 pixels of a row: 3 x 10 loads for 8 patterns. A pixel another
+// thread zeroes concurrently reads as v (|v| < cutoff) or 0 -- the same mask bit either way.
+__global__ void __launch_bounds__(256)
+k_form_patterns(float* __restrict__ frames, float cutoff, uint16_t* __restrict__ pat, int N, int H, int W) {
+    const int EH = H - 2, EW = W - 2, segs = (EW + 7) / 8;
+    const long long total = (long long)N * EH * segs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int sg = (int)(i % segs), ey = (int)((i / segs) % EH);
+        const long long n = i / ((long long)segs * EH);
+        const int x0 = sg * 8;
+        float* base = frames + (n * H + ey) * (long long)W + x0;
+        unsigned rowbits[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            unsigned bits = 0;
+            // this thread owns (zeroes) row ey of its columns; the last row of threads also owns the two rows below, the last
+            // segment also the two columns past its patterns
+            const bool own_row = r == 0 || ey == EH - 1;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                if (x0 + j < W) {
+                    float* q = base + (long long)r * W + j;
+                    const float v = *q;
+                    const bool small = fabsf(v) < cutoff;          // NaN compares false and stays (F8b)
+                    if (small && v != 0.f && own_row && (j < 8 || sg == segs - 1)) *q = 0.f;
+                    bits |= ((!small && v != 0.f) ? 1u : 0u) << j;
+                }
+            }
+            rowbits[r] = bits;
+        }
+        uint16_t* o = pat + (n * EH + ey) * (long long)EW + x0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (x0 + j < EW)
+                o[j] = (uint16_t)(((rowbits[0] >> j) & 7u) | (((rowbits[1] >> j) & 7u) << 3) | (((rowbits[2] >> j) & 7u) << 6));
+    }
+}
+
 struct StemE12Args {
     const uint16_t* pat;      // [N, Hp-2, Wp-2] 3x3 mask patterns of the e11 pixels
     const float* stem_w;      // unet_e11.weight [32][9]
@@ -698,8 +751,9 @@ static int launch_halo_ws(const void* x, const void* w, const HaloArgs& p, cudaS
 using namespace evfly;
 
 static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp, int Wp,
-                     int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream, int pad = 0) {
-    EVFLY_REQUIRE(d_x && d_w && d_out && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
+                     int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream, int pad = 0, const float* d_w1 = nullptr,
+                     const float* d_b1 = nullptr, float* d_out1 = nullptr) {
+    EVFLY_REQUIRE(d_x && d_w && (d_out || d_out1) && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
     EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128) || (Cin == 128 && (Cout == 64 || Cout == 128 || Cout == 256)),
                   "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64}, (64,128) or (128, 64|128|256) (got %d, %d)", Cin, Cout);
     HaloArgs p;
@@ -717,6 +771,11 @@ static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(d_pool);
     p.Hp2 = Hp2;
     p.Wp2 = Wp2;
+    p.w1 = d_w1;
+    p.b1 = d_b1;
+    p.out1 = d_out1;
+    EVFLY_REQUIRE((d_w1 == nullptr) == (d_out1 == nullptr) && (d_w1 == nullptr) == (d_b1 == nullptr), "tc_conv3x3_halo_out1_bf16: w1 / b1 / out1 go together");
+    EVFLY_REQUIRE(d_out || !d_pool, "tc_conv3x3_halo_bf16: the fused pool needs the conv output");
     EVFLY_REQUIRE(!d_pool || (Hp2 >= (vh - 2) / 2 && Wp2 >= (vw - 2) / 2), "tc_conv3x3_halo_pool_bf16: pooled grid smaller than (vh-2)/2 x (vw-2)/2");
     EVFLY_REQUIRE((long long)p.tiles_x * p.tiles_y * N < (1ll << 31), "tc_conv3x3_halo_bf16: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;
@@ -741,6 +800,13 @@ extern "C" int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w,
     return halo_conv(d_x, d_w, d_bias, d_out, d_pool, N, Hp, Wp, vh, vw, Cin, Cout, relu, Hp2, Wp2, stream);
 }
 
+extern "C" int evfly_tc_conv3x3_halo_out1_bf16(const void* d_x, const void* d_w, const float* d_bias, const float* d_w1, const float* d_b1, float* d_out1,
+                                               int N, int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, void* stream) {
+    EVFLY_REQUIRE(d_w1 && d_b1 && d_out1, "tc_conv3x3_halo_out1_bf16: null pointer");
+    EVFLY_REQUIRE((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64), "tc_conv3x3_halo_out1_bf16: Cin, Cout in {32, 64}");
+    return halo_conv(d_x, d_w, d_bias, nullptr, nullptr, N, Hp, Wp, vh, vw, Cin, Cout, relu, 0, 0, stream, 0, d_w1, d_b1, d_out1);
+}
+
 extern "C" int evfly_tc_conv3x3_same_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int H, int W, int Cin,
                                           int Cout, int relu, void* stream) {
     return halo_conv(d_x, d_w, d_bias, d_out, nullptr, N, H, W, H, W, Cin, Cout, relu, 0, 0, stream, 1);
@@ -751,6 +817,15 @@ extern "C" int evfly_stem_patterns(const float* d_mask, uint16_t* d_pat, int N, 
     if (N == 0) return EVFLY_OK;
     const long long total = (long long)N * (H - 2) * (W - 2);
     k_stem_patterns<<<stream_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(d_mask, d_pat, N, H, W);
+    EVFLY_LAUNCHED();
+    return EVFLY_OK;
+}
+
+extern "C" int evfly_form_patterns(float* d_frames, float cutoff, uint16_t* d_pat, int N, int H, int W, void* stream) {
+    EVFLY_REQUIRE(d_frames && d_pat && N >= 0 && H >= 3 && W >= 3, "form_patterns: bad argument");
+    if (N == 0) return EVFLY_OK;
+    const long long total = (long long)N * (H - 2) * ((W - 2 + 7) / 8);
+    k_form_patterns<<<stream_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(d_frames, cutoff, d_pat, N, H, W);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
 }
@@ -775,6 +850,9 @@ extern "C" int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d
     p.Wp2 = Wp2;
     EVFLY_REQUIRE(!d_pool || (Hp2 >= (H - 4) / 2 && Wp2 >= (W - 4) / 2), "tc_stem_e12_pool_bf16: pooled grid smaller than (H-4)/2 x (W-4)/2");
     EVFLY_REQUIRE((long long)p.tiles_x * p.tiles_y * N < (1ll << 31), "tc_stem_e12_pool_bf16: too many tiles");
+    p.w1 = nullptr;
+    p.b1 = nullptr;
+    p.out1 = nullptr;
     StemE12Args sa;
     sa.pat = d_pat;
     sa.stem_w = d_stem_w;

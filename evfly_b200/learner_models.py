@@ -283,6 +283,7 @@ class OrigUNet(PackedModule):
         for i in range(1, 5):
             bf[f"up{i}"] = tc.pack_convt2x2_weight(getattr(self, f"unet_upconv{i}").weight)
         bf["out"] = tc.pack_conv1x1_weight(self.unet_out.weight)
+        bf["out_w1"] = self.unet_out.weight.reshape(-1).to(tc.BF16).float().contiguous()     # bf16-rounded, for d42's epilogue
         if self.num_recurrent[0] > 0:
             bf["lstm"] = []
             for cell in self.lstm.cell_list:
@@ -313,7 +314,7 @@ class OrigUNet(PackedModule):
             w.conv_w[i], w.conv_b[i] = p(bf[name]), p(getattr(self, "unet_" + name).bias.float())
         for i in range(4):
             w.up_w[i], w.up_b[i] = p(bf[f"up{i + 1}"]), p(getattr(self, f"unet_upconv{i + 1}").bias.float())
-        w.out_w, w.out_b = p(bf["out"]), p(self.unet_out.bias.float())
+        w.out_w, w.out_b = p(bf["out_w1"]), p(self.unet_out.bias.float())
         w.lstm_wx, w.lstm_wh = p(bf["lstm"][0][0]), p(bf["lstm"][0][1])
         return w, keep
 
@@ -428,7 +429,8 @@ class OrigUNet(PackedModule):
         cvp = lambda g, name: tc.conv3x3_pool(g, W[name], b(name), relu=True)     # conv + MaxPool2d(2), fused where it can be
         if self.form_BEV == 2 and tc.FUSE_STEM and tc.USE_HALO and tc.FUSE_POOL and im.shape[1] == 1:
             # binary mask: unet_e11 is a 512-entry table lookup inside the e12 kernel, e11 never goes to HBM
-            y_e1, p1 = tc.stem_e12_pool(im, self.unet_e11.weight, self.unet_e11.bias, W["e12"], b("e12"))
+            y_e1, p1 = tc.stem_e12_pool(im, self.unet_e11.weight, self.unet_e11.bias, W["e12"], b("e12"),
+                                        frames_cutoff=float(self.evs_min_cutoff) if getattr(self, "_fold_form_input", False) else None)
         else:
             y_e1, p1 = cvp(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12")
         y_e2, p2 = cvp(cv(p1, "e21"), "e22")
@@ -461,11 +463,20 @@ class OrigUNet(PackedModule):
                     else:
                         raise ValueError(f'[LEARNER_MODELS/ORIGUNET] skip_type should be crop/interp/none, but is {self.skip_type}.')
                     tc.conv_transpose2x2(y, W[f"up{lvl}"], up.bias, cat, C)
-                y = cv(cv(tc.Grid(cat, oh, ow), f"d{lvl}1"), f"d{lvl}2")
+                if lvl == 4 and self.num_out_channels == 1 and tc.USE_HALO:
+                    # unet_d42 with unet_out (1x1 to one channel) in its epilogue: the 32-channel activation is never written
+                    y1 = cv(tc.Grid(cat, oh, ow), "d41")
+                    out32 = tc.conv3x3_out1(y1, W["d42"], b("d42"), W["out_w1"], self.unet_out.bias)
+                    y = tc.Grid(out32.view(N, oh, ow, 1), oh - 4, ow - 4)
+                else:
+                    y = cv(cv(tc.Grid(cat, oh, ow), f"d{lvl}1"), f"d{lvl}2")
             if self.num_out_channels != 1:
                 raise NotImplementedError("num_out_channels == 2 is not used by any shipped configuration")
-            out32 = torch.empty((y.rows, 1), dtype=torch.float32, device=dev)
-            tc.gemm(y.data.view(y.rows, y.C), W["out"], self.unet_out.bias, out_f32=out32)
+            if y.data.dtype == torch.float32:
+                out32 = y.data
+            else:
+                out32 = torch.empty((y.rows, 1), dtype=torch.float32, device=dev)
+                tc.gemm(y.data.view(y.rows, y.C), W["out"], self.unet_out.bias, out_f32=out32)
             y_upconv = tc.grid_to_nchw(out32.view(N, y.Hp, y.Wp, 1), y.vh, y.vw)
             y_interp = ops.resize_bilinear(y_upconv, (self.input_h, self.input_w), align_corners=False)
         return (lambda: tc.grid_to_nchw(y_e5.data, y_e5.vh, y_e5.vw)), h_unet, y_upconv, y_interp
@@ -519,7 +530,10 @@ class OrigUNet(PackedModule):
         if x[2] is None:
             x[2] = (None, None)
         use_stage = self.precision == 'bf16' and tc.USE_STAGE_ABI and pk["stage"] is not None and tuple(im.shape[1:]) == (1, self.input_h, self.input_w)
-        if not use_stage and (self.num_in_channels == 2 or self.form_BEV > 0):
+        # binary input on the bf16 path: form_input is folded into the stem's pattern extraction (same in-place cutoff)
+        self._fold_form_input = (not use_stage and self.precision == 'bf16' and self.form_BEV == 2 and tc.FUSE_STEM and tc.USE_HALO and tc.FUSE_POOL
+                                 and im.shape[1] == 1)
+        if not use_stage and not self._fold_form_input and (self.num_in_channels == 2 or self.form_BEV > 0):
             im = self.form_input(im)
 
         if use_stage:

@@ -402,15 +402,34 @@ def _call_stem_e12(*args):
     _lib.check(_lib.load().evfly_tc_stem_e12_pool_bf16(*args, _lib.stream_ptr()), "evfly_tc_stem_e12_pool_bf16")
 
 
-def stem_e12_pool(mask_f32, stem_w, stem_b, w_packed, bias, relu=True):
-    """Binary mask [N,1,H,W] -> (y_e1 grid, pooled grid): unet_e11 + unet_e12 + MaxPool2d(2) without e11 in HBM."""
+def stem_e12_pool(mask_f32, stem_w, stem_b, w_packed, bias, relu=True, frames_cutoff=None):
+    """Binary mask [N,1,H,W] -> (y_e1 grid, pooled grid): unet_e11 + unet_e12 + MaxPool2d(2) without e11 in HBM.
+    frames_cutoff = c: the first argument is the NORMALISED FRAME instead; form_input's cutoff (in place, like the reference)
+    and the mask are folded into the pattern extraction (one pass, no mask tensor)."""
     N, _, H, W = mask_f32.shape
     dev = mask_f32.device
     pat = torch.empty((N, H - 2, W - 2), dtype=torch.int16, device=dev)
-    _lib.check(_lib.load().evfly_stem_patterns(_lib.ptr(mask_f32), pat.data_ptr(), N, H, W, _lib.stream_ptr()), "evfly_stem_patterns")
+    if frames_cutoff is None:
+        _lib.check(_lib.load().evfly_stem_patterns(_lib.ptr(mask_f32), pat.data_ptr(), N, H, W, _lib.stream_ptr()), "evfly_stem_patterns")
+    else:
+        _lib.check(_lib.load().evfly_form_patterns(_lib.ptr(mask_f32), float(frames_cutoff), pat.data_ptr(), N, H, W, _lib.stream_ptr()), "evfly_form_patterns")
     out = new_grid(N, H, W, 32, H - 4, W - 4, dev)
     ph, pw = (H - 4) // 2, (W - 4) // 2
     pooled = new_grid(N, ph, pw, 32, ph, pw, dev)
     _call_stem_e12(pat.data_ptr(), _lib.ptr(stem_w.contiguous()), _lib.ptr(stem_b), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(),
                    pooled.data.data_ptr(), N, H, W, int(relu), pooled.Hp, pooled.Wp)
     return out, pooled
+
+
+def conv3x3_out1(g: Grid, w_packed, bias, w1_f32, b1, relu=True) -> torch.Tensor:
+    """3x3 valid conv (+bias, ReLU) followed by a 1x1 conv to one channel in the epilogue (unet_d42 + unet_out): fp32
+    [N, Hp, Wp] on g's pitch grid, valid (vh-2) x (vw-2); the Cout-channel activation is never written."""
+    Cout = w_packed.shape[0]
+    out = torch.empty((g.N, g.Hp, g.Wp), dtype=torch.float32, device=g.data.device)
+    _call_halo_out1(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), _lib.ptr(w1_f32), _lib.ptr(b1), out.data_ptr(), g.N, g.Hp, g.Wp,
+                    g.vh, g.vw, g.C, Cout, int(relu))
+    return out
+
+
+def _call_halo_out1(*args):
+    _lib.check(_lib.load().evfly_tc_conv3x3_halo_out1_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_out1_bf16")

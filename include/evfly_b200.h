@@ -530,6 +530,13 @@ int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w, const floa
 int evfly_tc_conv3x3_same_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int H, int W,
                                int Cin, int Cout, int relu, void* stream);
 
+/* The same conv followed by a 1x1 conv to ONE channel in the epilogue (unet_d42 + unet_out, learner_models.py:581-583):
+ * out1[n,oh,ow] = b1 + sum_c bf16(relu?(conv)[c]) * w1[c], fp32 on the [N,Hp,Wp] pitch grid; the Cout-channel activation
+ * is never written. d_w1 fp32 [Cout] (the 1x1 weights rounded to bf16, stored as fp32), d_b1 fp32 [1]. Cin, Cout in {32, 64}. */
+int evfly_tc_conv3x3_halo_out1_bf16(const void* d_x, const void* d_w, const float* d_bias, const float* d_w1,
+                                    const float* d_b1, float* d_out1, int N, int Hp, int Wp, int vh, int vw, int Cin,
+                                    int Cout, int relu, void* stream);
+
 /* vitfly_models.py:136-142: cat([PixelShuffle(2)(s2), Upsample((2*H2,2*W2), bilinear, align_corners=True)(s1)], 1)
  * from the bf16 token tensors t2 [B,H2,W2,C2], t1 [B,H1,W1,C1] into one dense bf16 NHWC tensor
  * [B,2*H2,2*W2,ld]: channels [0,C2/4) shuffle, [C2/4,C2/4+C1) upsample, [.., ld) zero.                 */
@@ -562,6 +569,9 @@ int evfly_vit_attn_bf16(const void* d_x, const void* d_kv, const void* d_w_img, 
  *       -> y_e1 bf16 NHWC on the [N,H,W,32] pitch grid (valid (H-4) x (W-4)) and, when d_pool is given, MaxPool2d(2) of it
  *       on the [N,Hp2,Wp2,32] grid (learner_models.py:533-535).                                                      */
 int evfly_stem_patterns(const float* d_mask, uint16_t* d_pat, int N, int H, int W, void* stream);
+/* form_input(form_BEV = 2) + evfly_stem_patterns in one pass over the normalised frames fp32 [N,1,H,W]: |x| < cutoff is zeroed
+ * IN PLACE like the reference does (learner_models.py:477) and the patterns are those of the mask x != 0 (NaN counts as set). */
+int evfly_form_patterns(float* d_frames, float cutoff, uint16_t* d_pat, int N, int H, int W, void* stream);
 int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w,
                                 const float* d_bias, void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2,
                                 int Wp2, void* stream);
@@ -585,7 +595,7 @@ int evfly_prep_frame(const uint8_t* d_u8, const int32_t* d_counts, int N, int H,
  *   conv_w[i] bf16 [Cout][9*Cin] (K index = (kh*3+kw)*Cin + ci), conv_b[i] fp32 [Cout], i = e12, e21, e22, e31,
  *       e32, e41, e42, e51, e52, d11, d12, d21, d22, d31, d32, d41, d42
  *   up_w[l] bf16 [4*Cout][Cin] (row = (2a+b)*Cout + co of ConvTranspose2d weight [Cin,Cout,a,b]), up_b[l] fp32 [Cout]
- *   out_w bf16 [1][32], out_b fp32 [1]                                                                (unet_out)
+ *   out_w fp32 [32] (unet_out.weight rounded to bf16, stored as fp32), out_b fp32 [1]      (unet_out, in d42's epilogue)
  *   lstm_wx / lstm_wh bf16 [2048][512]: the x / h halves of lstm.cell_list.0.conv.weight with rows interleaved
  *       n = 4*ch + gate (gate order i,f,o,g, convlstm.py:44)                                                  */
 typedef struct evfly_unet_weights {
@@ -595,7 +605,7 @@ typedef struct evfly_unet_weights {
     const float* conv_b[17];
     const void*  up_w[4];
     const float* up_b[4];
-    const void*  out_w;
+    const float* out_w;
     const float* out_b;
     const void*  lstm_wx;
     const void*  lstm_wh;

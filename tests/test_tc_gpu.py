@@ -343,3 +343,39 @@ def test_stem_lookup_fused_into_e12(cuda_lib, N, H, W):
     ref_out, ref_pool = tc.conv3x3_pool(tc.stem_conv3x3(mask.cuda(), w1.cuda(), b1.cuda()), tc.pack_conv3x3_weight(w2.cuda()), b2.cuda())
     d = (tc.grid_to_nchw(out.data, H - 4, W - 4) - tc.grid_to_nchw(ref_out.data, H - 4, W - 4)).abs()
     assert d.max().item() <= 3e-2 and d.mean().item() <= 1e-3       # e11 values may differ by one bf16 ulp (summation order)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 24, 40, 32, 32), (1, 72, 152, 32, 32), (1, 19, 11, 64, 64)])
+def test_conv3x3_with_fused_1x1_output(cuda_lib, N, H, W, Cin, Cout):
+    """unet_d42 + unet_out (learner_models.py:581-583): 3x3 valid conv + ReLU with the 1x1 conv to one channel in the epilogue."""
+    x = bf(rnd(N, Cin, H, W, seed=1))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5))
+    b = rnd(Cout, seed=3)
+    w1, b1 = bf(rnd(Cout, seed=4, scale=Cout ** -0.5)), rnd(1, seed=5)
+    act = F.relu(F.conv2d(x.double(), w.double(), b.double())).to(BF).double()          # the epilogue rounds the activation to bf16 first
+    want = (act * w1.double().view(1, -1, 1, 1)).sum(1) + b1.double()
+    g = tc.nchw_to_grid(x.cuda(), H, W)
+    out = tc.conv3x3_out1(g, tc.pack_conv3x3_weight(w.cuda()), b.cuda(), w1.cuda(), b1.cuda())
+    got = out[:, :H - 2, :W - 2].cpu().double()
+    assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+
+
+def test_form_patterns_equals_form_input_then_patterns(cuda_lib):
+    """evfly_form_patterns = form_input(form_BEV = 2) + evfly_stem_patterns in one pass: same patterns, same in-place cutoff
+    of the caller's frames (learner_models.py:477), NaN pixels count as set (F8b)."""
+    from evfly_b200 import _lib, ops
+    g = torch.Generator().manual_seed(9)
+    N, H, W = 3, 41, 53
+    fr = (torch.randn(N, 1, H, W, generator=g) * (torch.rand(N, 1, H, W, generator=g) < 0.4)).cuda()
+    fr[0, 0, 5, 7] = float("nan")
+    fr[1, 0, H - 1, W - 1] = 5e-4              # a corner pixel below the cutoff: owned by the last thread row / segment
+    fr[2, 0, H - 2, 3] = -5e-4
+    a = fr.clone()
+    mask = ops.form_input(a, 2, 1e-3)
+    pat_a = torch.empty((N, H - 2, W - 2), dtype=torch.int16, device="cuda")
+    _lib.check(cuda_lib.evfly_stem_patterns(_lib.ptr(mask), pat_a.data_ptr(), N, H, W, _lib.stream_ptr()))
+    b = fr.clone()
+    pat_b = torch.empty_like(pat_a)
+    _lib.check(cuda_lib.evfly_form_patterns(_lib.ptr(b), 1e-3, pat_b.data_ptr(), N, H, W, _lib.stream_ptr()))
+    assert torch.equal(pat_a, pat_b)
+    assert torch.equal(torch.nan_to_num(a, nan=123.0), torch.nan_to_num(b, nan=123.0))
