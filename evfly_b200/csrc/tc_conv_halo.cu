@@ -15,6 +15,13 @@
 // warp 0 lane 0: TMA producer (halo ring) | warp 1 lane 0: MMA issuer | warp 2: TMEM alloc |
 // warps 4-11: epilogue in two groups of 4 warps that alternate tiles (+bias, ReLU, bf16, masked 64/128-byte
 // stores to the valid pixels): one warp per SM sub-partition was latency-bound at ~1 us per tile
+//
+// Round 2 (profiles/r2_exp_halo_roles.txt: with each role in turn reduced to its barrier traffic, the 32-channel layers
+// were bound by the INSTRUCTION COUNT of the epilogue and of the tile bookkeeping, ~3500 warp instructions per 128-pixel
+// tile against 720 clk of MMA): the epilogue converts with cvt.rn[.relu].bf16x2 (one instruction per channel pair, ReLU
+// included), pools from the staging rows it writes anyway (4 LDS + 12 packed max instead of 64 shuffles + 64 max), no role
+// divides per tile (TileWalk), and the layers whose weights + halos fit twice run 2 CTAs per SM so that one CTA's
+// handshake latency is covered by the other's MMAs.
 #include "tc_common.cuh"
 
 namespace evfly {
@@ -27,6 +34,7 @@ struct HaloArgs {
     int pad;              // 1: padding=1 conv on a dense tensor (Hp x Wp all valid): the halo box starts at (-1,-1) and TMA zero-fills outside the image
     int N, Hp, Wp, out_vh, out_vw;
     int tiles_x, tiles_y;
+    uint32_t magic_x;     // floor(2^32 / tiles_x) + 1 when tiles_x * tiles_y < 65536 (then umulhi(rem, magic_x) == rem / tiles_x), else 0
     int relu;
     // optional fused 1x1 output conv to ONE channel (unet_out after unet_d42, learner_models.py:583): out1[n, oh, ow] =
     // b1 + sum_c bf16(act(conv)[c]) * w1[c] in fp32 on the same pitch grid; with it `out` may be null (the COUT-channel
@@ -43,26 +51,21 @@ struct HaloCfg {
     static constexpr int HALO_BYTES = ((HALO_ROWS * ROW_B + 1023) / 1024) * 1024;
     static constexpr int W_TAP_BYTES = COUT * ROW_B;
     static constexpr int W_BYTES = 9 * W_TAP_BYTES;
-    static constexpr int STAGES = (COUT > 64) ? 3 : 4;          // 64->128: 144 KB of resident weights leave room for 3 halos
+    // 2 CTAs per SM where weights + halo ring + staging fit in half the shared memory (32->32, 32->64, 64->32): a second
+    // CTA's MMAs fill the tensor pipe while the first waits on its own producer/epilogue handshakes
+    static constexpr int MINB = (CIN == 32 || (CIN == 64 && COUT == 32)) ? 2 : 1;
+    static constexpr int STAGES = (MINB == 2) ? (CIN == 32 ? 3 : 2) : (COUT > 64) ? 3 : 4;   // 64->128: 144 KB of resident weights leave room for 3 halos
     static constexpr int NACC = 4;
     static constexpr int TMEM_COLS = (NACC * COUT <= 128) ? 128 : (NACC * COUT <= 256) ? 256 : 512;
     // epilogue staging (8 warps x 32 pixels x COUT bf16) so that global stores are 512-byte contiguous; not for COUT = 128
     static constexpr int OUT_STAGE_BYTES = (COUT <= 64) ? 8 * 32 * COUT * 2 : 0;
     static constexpr int SMEM_BYTES = W_BYTES + STAGES * HALO_BYTES + 1024 /*alignment slack*/ + 2048 /*barriers, bias*/ + OUT_STAGE_BYTES;
     static_assert(SMEM_BYTES <= 227 * 1024, "halo conv: weights + halo stages exceed shared memory");
+    static_assert(MINB == 1 || 2 * (SMEM_BYTES + 1024) <= 227 * 1024, "halo conv: two CTAs per SM do not fit");
     static constexpr uint32_t LAYOUT = (CIN == 64) ? kLayoutSw128 : kLayoutSw64;
     static constexpr uint32_t SBO_A = 10 * ROW_B;               // next 8-pixel group = next output row = 10 halo rows
     static constexpr uint32_t SBO_B = 8 * ROW_B;
 };
-
-__device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
-    uint4 pk;
-    __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-    __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-    return pk;
-}
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -82,6 +85,49 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// two fp32 -> one packed bf16x2 (lo = first channel), round-to-nearest-even; the .relu form clamps negatives to +0 first and
+// keeps NaN (as torch's relu does)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint4 max4_bf16x2(const uint4& a, const uint4& b) {
+    return make_uint4(max_bf16x2(a.x, b.x), max_bf16x2(a.y, b.y), max_bf16x2(a.z, b.z), max_bf16x2(a.w, b.w));
+}
+
+// Position of a role in its strided walk over the tiles (tile = n * tiles_per_img + rem) without a division per tile:
+// the stride is split once into whole images and a remainder.
+struct TileWalk {
+    int n, rem, step_n, step_rem, tpi;
+    __device__ __forceinline__ TileWalk(long long first, long long step, int tiles_per_img) {
+        tpi = tiles_per_img;
+        n = (int)(first / tiles_per_img);
+        rem = (int)(first - (long long)n * tiles_per_img);
+        step_n = (int)(step / tiles_per_img);
+        step_rem = (int)(step - (long long)step_n * tiles_per_img);
+    }
+    __device__ __forceinline__ void next() {
+        n += step_n;
+        rem += step_rem;
+        if (rem >= tpi) { rem -= tpi; ++n; }
+    }
+    __device__ __forceinline__ void yx(const HaloArgs& p, int& ty, int& tx) const {
+        ty = p.magic_x ? (int)__umulhi((unsigned)rem, p.magic_x) : rem / p.tiles_x;
+        tx = rem - ty * p.tiles_x;
+    }
+};
+
 // Epilogue shared by the two halo kernels: warps 4-7 take the even local tiles, warps 8-11 the odd ones.
 template <int COUT, int NACC, bool STAGE_OUT>
 __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int lane, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -94,27 +140,19 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
     constexpr bool kStage = STAGE_OUT;
     constexpr int kCP = COUT / 8;            // 16-byte chunks per pixel
     const uint32_t my_stage = smem_u32(s_ostage) + (warp - 4) * (32 * COUT * 2);      // shared-space address: STS / LDS, not generic ST / LD
-    constexpr bool kBiasRegs = COUT <= 64;   // bias in registers (same for every tile); from shared memory for wide outputs
-    float breg[kBiasRegs ? COUT : 1];
-    if constexpr (kBiasRegs) {
-#pragma unroll
-        for (int j = 0; j < COUT; ++j) breg[j] = s_bias[j];
-    }
+    const uint32_t my_row = my_stage + lane * (COUT * 2);
+    const uint32_t my_swz = kCP == 4 ? ((lane >> 1) & 3) : (lane & 7);
+    const float4* s_bias4 = reinterpret_cast<const float4*>(s_bias);                   // broadcast reads: registers are what two CTAs per SM are short of
+    TileWalk tw((long long)blockIdx.x + (long long)grp * gridDim.x, 2ll * gridDim.x, tiles_per_img);
     int it = grp;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+    for (long long tile = (long long)blockIdx.x + (long long)grp * gridDim.x; tile < total_tiles; tile += 2ll * gridDim.x, it += 2, tw.next()) {
         const int acc = it & (NACC - 1);
         const uint32_t acc_phase = (uint32_t)(it / NACC) & 1u;
-        const int n = tile / tiles_per_img;
-        const int rem = tile - n * tiles_per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int n = tw.n;
+        int ty, tx;
+        tw.yx(p, ty, tx);
         const int oh = ty * 16 + r, ow = tx * 8 + c;
         const bool ok = oh < p.out_vh && ow < p.out_vw;
-        __nv_bfloat16* o = p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT;
-        // fused 2x2 max-pool: the partners of pixel (r, c) are lanes ^1 (column) and ^8 (row) of the same warp;
-        // the lane with even r and even c writes. max commutes with the (monotonic) bf16 rounding, so the
-        // result is bit-identical to pooling the stored tensor.
-        const bool pool_lane = p.pool_out != nullptr && ((lane & 9) == 0) && oh + 1 < p.out_vh && ow + 1 < p.out_vw;
-        __nv_bfloat16* po = p.pool_out ? p.pool_out + (((long long)n * p.Hp2 + (oh >> 1)) * p.Wp2 + (ow >> 1)) * COUT : nullptr;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         float dot1 = 0.f;
@@ -123,40 +161,75 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * COUT + c0), v);
             tmem_ld_wait();
+            uint32_t pk[16];                 // channels c0 + 2i, c0 + 2i + 1
+            if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = s_bias4[(c0 >> 2) + i];
+                    pk[2 * i] = cvt_relu_bf16x2(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y);
+                    pk[2 * i + 1] = cvt_relu_bf16x2(__uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = s_bias4[(c0 >> 2) + i];
+                    pk[2 * i] = cvt_bf16x2(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y);
+                    pk[2 * i + 1] = cvt_bf16x2(__uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w);
+                }
+            }
+            if (p.w1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    dot1 = fmaf(__uint_as_float(pk[i] << 16), __ldg(p.w1 + c0 + 2 * i), dot1);
+                    dot1 = fmaf(__uint_as_float(pk[i] & 0xffff0000u), __ldg(p.w1 + c0 + 2 * i + 1), dot1);
+                }
+            }
+            if (!p.out) continue;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float x = __uint_as_float(v[q * 8 + e]) + (kBiasRegs ? breg[kBiasRegs ? c0 + q * 8 + e : 0] : s_bias[c0 + q * 8 + e]);
-                    f[e] = p.relu ? fmaxf(x, 0.f) : x;
-                }
-                if (p.w1) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) dot1 = fmaf(__bfloat162float(__float2bfloat16_rn(f[e])), __ldg(p.w1 + c0 + q * 8 + e), dot1);
-                }
-                if (!p.out) continue;
+                const uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 if constexpr (kStage) {
                     // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
-                    sts128(my_stage + lane * (COUT * 2) + ((((c0 >> 3) + q) ^ (kCP == 4 ? ((lane >> 1) & 3) : (lane & 7))) << 4), pack8_bf16(f));
+                    sts128(my_row + (((uint32_t)((c0 >> 3) + q) ^ my_swz) << 4), val);
                 } else {
-                    if (ok) reinterpret_cast<uint4*>(o + c0)[q] = pack8_bf16(f);
-                }
-                if (p.pool_out) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
-                        f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 8));
+                    if (ok) reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT + c0)[q] = val;
+                    if (p.pool_out) {
+                        // fused 2x2 max-pool: the partners of pixel (r, c) are lanes ^1 (column) and ^8 (row) of the same warp; the
+                        // lane with even r and even c writes. max commutes with the (monotonic) bf16 rounding, so the result
+                        // is bit-identical to pooling the stored tensor.
+                        uint4 m = max4_bf16x2(val, make_uint4(__shfl_xor_sync(0xffffffffu, val.x, 1), __shfl_xor_sync(0xffffffffu, val.y, 1),
+                                                              __shfl_xor_sync(0xffffffffu, val.z, 1), __shfl_xor_sync(0xffffffffu, val.w, 1)));
+                        m = max4_bf16x2(m, make_uint4(__shfl_xor_sync(0xffffffffu, m.x, 8), __shfl_xor_sync(0xffffffffu, m.y, 8),
+                                                      __shfl_xor_sync(0xffffffffu, m.z, 8), __shfl_xor_sync(0xffffffffu, m.w, 8)));
+                        if (((lane & 9) == 0) && oh + 1 < p.out_vh && ow + 1 < p.out_vw)
+                            reinterpret_cast<uint4*>(p.pool_out + (((long long)n * p.Hp2 + (oh >> 1)) * p.Wp2 + (ow >> 1)) * COUT + c0)[q] = m;
                     }
-                    if (pool_lane) reinterpret_cast<uint4*>(po + c0)[q] = pack8_bf16(f);
                 }
             }
         }
         if (p.w1 && ok) p.out1[((long long)n * p.Hp + oh) * p.Wp + ow] = dot1 + __ldg(p.b1);
         if constexpr (kStage) if (p.out) {
+            __syncwarp();
+            if (p.pool_out) {
+                // fused 2x2 max-pool from the staging rows: the warp's 4 x 8 pixels hold 2 x 4 pooled pixels of kCP chunks; one
+                // (pooled pixel, chunk) per lane and pass. Lanes of odd pooled pixels read the odd column first, so that the eight
+                // lanes of a shared-memory phase cover all eight 16-byte bank groups (COUT = 32: two pixels per 128 bytes). max
+                // commutes with the (monotonic) bf16 rounding: bit-identical to pooling the stored tensor.
+#pragma unroll
+                for (int j = 0; j < kCP / 4; ++j) {
+                    const int id = j * 32 + lane, pp = id / kCP, ch = id % kCP;
+                    const int pr = pp >> 2, pc = pp & 3, f = pp & 1;
+                    const int px0 = pr * 16 + pc * 2;
+                    auto at = [&](int px) { return lds128(my_stage + px * (COUT * 2) + (((uint32_t)ch ^ (uint32_t)(kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4)); };
+                    const uint4 a0 = at(px0 + f), a1 = at(px0 + (f ^ 1)), a2 = at(px0 + 8 + f), a3 = at(px0 + 8 + (f ^ 1));
+                    const uint4 m = max4_bf16x2(max4_bf16x2(a0, a1), max4_bf16x2(a2, a3));
+                    const int ph = ty * 8 + ew * 2 + pr, pw = tx * 4 + pc;
+                    if (2 * ph + 1 < p.out_vh && 2 * pw + 1 < p.out_vw)
+                        *reinterpret_cast<uint4*>(p.pool_out + (((long long)n * p.Hp2 + ph) * p.Wp2 + pw) * COUT + ch * 8) = m;
+                }
+            }
             // write-out: instruction j stores chunks [32j, 32j+32) of the warp's 32 pixels = 512 contiguous bytes
             // (8 pixels of one output row are adjacent in the NHWC grid)
-            __syncwarp();
 #pragma unroll
             for (int j = 0; j < kCP; ++j) {
                 const int id = j * 32 + lane, px = id / kCP, ch = id % kCP;
@@ -175,7 +248,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
 }
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(384, (HaloCfg<CIN, COUT>::MINB))
 k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloArgs p) {
     using Cfg = HaloCfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
@@ -189,7 +262,7 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t* tempty_bar = tfull_bar + Cfg::NACC;         // [NACC]
     uint64_t* w_bar = tempty_bar + Cfg::NACC;             // [1]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
-    float* s_bias = reinterpret_cast<float*>(w_bar + 2);  // [COUT]
+    float* s_bias = reinterpret_cast<float*>(bars + 32);  // 16-byte aligned: the epilogue reads it as float4  // [COUT]
     uint8_t* s_ostage = s_halo + Cfg::STAGES * Cfg::HALO_BYTES + 2048;   // [8 warps][32 px][COUT] bf16 (16-byte chunks XOR-swizzled)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,13 +298,13 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * Cfg::W_TAP_BYTES, &map_w, w_bar, t * CIN, 0);
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n = tile / tiles_per_img;
-            const int rem = tile - n * tiles_per_img;
-            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        TileWalk tw(blockIdx.x, gridDim.x, tiles_per_img);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next()) {
+            int ty, tx;
+            tw.yx(p, ty, tx);
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], Cfg::HALO_ROWS * Cfg::ROW_B);
-            tma_load_4d(s_halo + stage * Cfg::HALO_BYTES, &map_x, &full_bar[stage], 0, tx * 8 - p.pad, ty * 16 - p.pad, n);
+            tma_load_4d(s_halo + stage * Cfg::HALO_BYTES, &map_x, &full_bar[stage], 0, tx * 8 - p.pad, ty * 16 - p.pad, tw.n);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
@@ -319,7 +392,7 @@ k_tc_conv3x3_halo_ws(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint64_t* tfull_bar = b_empty + Cfg::NB;              // [NACC]
     uint64_t* tempty_bar = tfull_bar + Cfg::NACC;         // [NACC]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + Cfg::NACC);
-    float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);       // [COUT]
+    float* s_bias = reinterpret_cast<float*>(bars + 64);               // [COUT], 16-byte aligned: the epilogue reads it as float4
     uint8_t* s_ostage = s_b + Cfg::NB * Cfg::B_BLOCK + 2048;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -356,11 +429,13 @@ k_tc_conv3x3_halo_ws(const __grid_constant__ CUtensorMap map_x, const __grid_con
         int slot = 0;
         uint32_t b_phase = 0;
         int it = 0;
+        TileWalk tw(blockIdx.x, gridDim.x, tiles_per_img);      // load_halo is called once per tile, in tile order
         auto load_halo = [&](int tile, int j) {       // j = running local tile index -> buffer j & 1
             const int buf = j & 1;
-            const int n = tile / tiles_per_img;
-            const int rem = tile - n * tiles_per_img;
-            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            const int n = tw.n;
+            int ty, tx;
+            tw.yx(p, ty, tx);
+            tw.next();
             mbar_wait(&a_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
             mbar_expect_tx(&a_full[buf], 2 * 180 * 128);
             tma_load_4d(s_a + (buf * 2 + 0) * Cfg::CHUNK_BYTES, &map_x, &a_full[buf], 0, tx * 8 - p.pad, ty * 16 - p.pad, n);
@@ -501,11 +576,11 @@ struct StemE12Args {
     const float* stem_b;      // [32]
 };
 
-constexpr int kStemProducers = 96;      // warps 0, 2, 3
-constexpr int kLutRowB = 80;            // 64 bytes of e11 values + 16 of padding: consecutive patterns start 20 banks apart
-                                        // (unpadded, every lane of a 16-byte table read hit one of two 4-bank groups: 16-way conflicts, ncu r2_stem_e12)
+constexpr int kStemProducerWarps = 3;   // warps 0, 2, 3: each assembles every third tile of the CTA on its own
+constexpr int kLutRowB = 64;            // one table row = 32 bf16; the 16-byte chunks of a row are read in a lane-rotated order, which
+                                        // spreads a warp's reads over the banks (same chunk from every lane: 16-way conflicts, ncu r2_stem_e12)
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(384, 2)
 k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const StemE12Args sa) {
     using Cfg = HaloCfg<32, 32>;
     extern __shared__ uint8_t smem_raw[];
@@ -519,9 +594,9 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
     uint64_t* tempty_bar = tfull_bar + Cfg::NACC;
     uint64_t* w_bar = tempty_bar + Cfg::NACC;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
-    float* s_bias = reinterpret_cast<float*>(w_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(bars + 32);  // 16-byte aligned: the epilogue reads it as float4
     uint8_t* s_ostage = s_halo + Cfg::STAGES * Cfg::HALO_BYTES + 2048;
-    uint8_t* s_lut = s_ostage + Cfg::OUT_STAGE_BYTES;     // [512] rows of 32 bf16 (64 B) at a pitch of kLutRowB
+    uint8_t* s_lut = s_ostage + Cfg::OUT_STAGE_BYTES;     // [512] rows of 32 bf16 (64 B)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -529,7 +604,7 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_w);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full_bar[s], kStemProducers / 32); // one arrival per producer warp, after every lane's proxy fence
+            mbar_init(&full_bar[s], 1);                   // the one producer warp that assembled the stage
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < Cfg::NACC; ++a) {
@@ -561,76 +636,63 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ================= halo producers: pattern -> table row -> swizzled operand row =================
-        const int pt_id = (warp == 0 ? 0 : warp - 1) * 32 + lane;            // 0..95
-        if (pt_id == 0) {
+        // Producer warp j assembles local tiles j, j + 3, ... on its own (180 halo pixels = 6 passes of 32 lanes), so the
+        // per-tile bookkeeping runs once per tile instead of once per warp and a warp has three tile times per halo.
+        const int pw = warp == 0 ? 0 : warp - 1;          // 0..2
+        if (pw == 0 && lane == 0) {
             mbar_expect_tx(w_bar, Cfg::W_BYTES);
             for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * Cfg::W_TAP_BYTES, &map_w, w_bar, t * 32, 0);
         }
         const int EH = p.Hp - 2, EW = p.Wp - 2;
         const uint32_t halo_u32 = smem_u32(s_halo), lut_u32 = smem_u32(s_lut);
-        // halo pixels of this thread: idx = pt_id and pt_id + 96 (180 per tile)
-        const int i0 = pt_id, i1 = pt_id + kStemProducers;
-        const int hy0 = i0 / 10, hx0 = i0 - hy0 * 10, hy1 = i1 / 10, hx1 = i1 - hy1 * 10;
-        auto fetch = [&](int tile, unsigned& q0, unsigned& q1) {
-            const int n = tile / tiles_per_img;
-            const int rem = tile - n * tiles_per_img;
-            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-            const uint16_t* base = sa.pat + (long long)n * EH * EW;
-            const int y0 = ty * 16 + hy0, x0 = tx * 8 + hx0, y1 = ty * 16 + hy1, x1 = tx * 8 + hx1;
-            q0 = (y0 < EH && x0 < EW) ? (unsigned)__ldg(base + (long long)y0 * EW + x0) : 0u;
-            q1 = (i1 < Cfg::HALO_ROWS && y1 < EH && x1 < EW) ? (unsigned)__ldg(base + (long long)y1 * EW + x1) : 0u;
-        };
-        // the patterns of the next kDepth tiles are kept in flight (registers): a tile's two 2-byte loads come from HBM
-        // (~1 us), far longer than assembling a halo takes, and with one tile of lookahead that latency was the whole kernel
-        constexpr int kDepth = 4;
-        unsigned qa[kDepth], qb[kDepth];
+        constexpr int kPasses = (Cfg::HALO_ROWS + 31) / 32;                    // 6
+        int hyx[kPasses];                                                      // halo pixel of (pass, lane): hy << 8 | hx
 #pragma unroll
-        for (int d = 0; d < kDepth; ++d) {
-            qa[d] = qb[d] = 0;
-            const long long tl = (long long)blockIdx.x + (long long)d * gridDim.x;
-            if (tl < total_tiles) fetch((int)tl, qa[d], qb[d]);
+        for (int k = 0; k < kPasses; ++k) {
+            const int idx = k * 32 + lane, hy = idx / 10;
+            hyx[k] = idx < Cfg::HALO_ROWS ? (hy << 8) | (idx - hy * 10) : -1;
         }
-        int stage = 0;
-        uint32_t phase = 0;
-        // unrolled by kDepth so that slot d of the lookahead is a FIXED register: rotating the values through moves would
-        // make the first move wait for a load issued one tile ago (the scoreboard tracks registers, not values)
-#pragma unroll 1
-        for (long long base = blockIdx.x; base < total_tiles; base += (long long)kDepth * gridDim.x) {
+        const long long first = (long long)blockIdx.x + (long long)pw * gridDim.x, step = (long long)kStemProducerWarps * gridDim.x;
+        TileWalk tw(first, step, tiles_per_img);
+        unsigned q[kPasses];
+        auto fetch = [&]() {       // the patterns of the tile tw points at (2-byte loads from HBM, ~1 us: issued one tile of this warp ahead)
+            int ty, tx;
+            tw.yx(p, ty, tx);
+            const uint16_t* base = sa.pat + (long long)tw.n * EH * EW;
 #pragma unroll
-          for (int d = 0; d < kDepth; ++d) {
-            const long long tile = base + (long long)d * gridDim.x;
-            if (tile >= total_tiles) break;
-            const unsigned q0 = qa[d], q1 = qb[d];
-            qa[d] = qb[d] = 0;
-            {
-                const long long tl = tile + (long long)kDepth * gridDim.x;
-                if (tl < total_tiles) fetch((int)tl, qa[d], qb[d]);
+            for (int k = 0; k < kPasses; ++k) {
+                const int y = ty * 16 + (hyx[k] >> 8), x = tx * 8 + (hyx[k] & 255);
+                q[k] = (hyx[k] >= 0 && y < EH && x < EW) ? (unsigned)__ldg(base + (long long)y * EW + x) : 0u;
             }
+        };
+        if (first < total_tiles) fetch();
+        int it = pw;
+        for (long long tile = first; tile < total_tiles; tile += step, it += kStemProducerWarps) {
+            const int stage = it % Cfg::STAGES;
+            const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
+            unsigned cur[kPasses];
+#pragma unroll
+            for (int k = 0; k < kPasses; ++k) cur[k] = q[k];
+            tw.next();
+            if (tile + step < total_tiles) fetch();
             mbar_wait(&empty_bar[stage], phase ^ 1);
             const uint32_t dst = halo_u32 + stage * Cfg::HALO_BYTES;
-            {   // chunk order rotated by lane: the four 16-byte reads of a warp instruction spread over all banks
-                const uint32_t src = lut_u32 + q0 * kLutRowB;
-                const uint32_t sw = (uint32_t)(i0 >> 1) & 3u;
-                uint4 v[4];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) v[cc] = lds128(src + ((((uint32_t)(cc + lane)) & 3u) << 4));
+            for (int k = 0; k < kPasses; ++k) {
+                const int idx = k * 32 + lane;
+                if (idx < Cfg::HALO_ROWS) {
+                    const uint32_t src = lut_u32 + cur[k] * kLutRowB;
+                    const uint32_t sw = (uint32_t)(idx >> 1) & 3u;
+                    uint4 v[4];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) sts128(dst + i0 * 64 + (((((uint32_t)(cc + lane)) & 3u) ^ sw) << 4), v[cc]);
-            }
-            if (i1 < Cfg::HALO_ROWS) {
-                const uint32_t src = lut_u32 + q1 * kLutRowB;
-                const uint32_t sw = (uint32_t)(i1 >> 1) & 3u;
-                uint4 v[4];
+                    for (int cc = 0; cc < 4; ++cc) v[cc] = lds128(src + ((((uint32_t)(cc + lane)) & 3u) << 4));
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) v[cc] = lds128(src + ((((uint32_t)(cc + lane)) & 3u) << 4));
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) sts128(dst + i1 * 64 + (((((uint32_t)(cc + lane)) & 3u) ^ sw) << 4), v[cc]);
+                    for (int cc = 0; cc < 4; ++cc) sts128(dst + idx * 64 + (((((uint32_t)(cc + lane)) & 3u) ^ sw) << 4), v[cc]);
+                }
             }
             fence_proxy_async();                                                   // this thread's generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);                          // the stage is full when the three producer warps have arrived
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-          }
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
         }
     } else if (warp == 1) {
         // ================= MMA issuer (as k_tc_conv3x3_halo) =================
@@ -724,7 +786,7 @@ static int launch_halo(const void* x, const void* w, const HaloArgs& p, cudaStre
     if (rc) return rc;
     EVFLY_SMEM_ATTR(Cfg::SMEM_BYTES, k_tc_conv3x3_halo<CIN, COUT>);
     const long long tiles = (long long)p.tiles_x * p.tiles_y * p.N;
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    const int grid = (int)(tiles < Cfg::MINB * kNumSMs ? tiles : Cfg::MINB * kNumSMs);
     k_tc_conv3x3_halo<CIN, COUT><<<grid, 384, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
     EVFLY_LAUNCHED();
     return EVFLY_OK;
@@ -746,6 +808,12 @@ static int launch_halo_ws(const void* x, const void* w, const HaloArgs& p, cudaS
     return EVFLY_OK;
 }
 
+static void set_tiles(HaloArgs& p) {
+    p.tiles_x = (p.out_vw + 7) / 8;
+    p.tiles_y = (p.out_vh + 15) / 16;
+    p.magic_x = (p.tiles_x > 1 && (long long)p.tiles_x * p.tiles_y < 65536) ? (uint32_t)((1ull << 32) / (unsigned)p.tiles_x) + 1u : 0u;
+}
+
 }  // namespace evfly
 
 using namespace evfly;
@@ -765,8 +833,7 @@ static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void
     p.pad = pad;
     p.out_vh = vh - 2 + 2 * pad;
     p.out_vw = vw - 2 + 2 * pad;
-    p.tiles_x = (p.out_vw + 7) / 8;
-    p.tiles_y = (p.out_vh + 15) / 16;
+    set_tiles(p);
     p.relu = relu;
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(d_pool);
     p.Hp2 = Hp2;
@@ -842,8 +909,7 @@ extern "C" int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d
     p.pad = 0;
     p.out_vh = H - 4;
     p.out_vw = W - 4;
-    p.tiles_x = (p.out_vw + 7) / 8;
-    p.tiles_y = (p.out_vh + 15) / 16;
+    set_tiles(p);
     p.relu = relu;
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(d_pool);
     p.Hp2 = Hp2;
@@ -862,9 +928,10 @@ extern "C" int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d
     CUtensorMap mw;
     const int rc = make_map_w(&mw, d_w, 32, 32);
     if (rc) return rc;
+    static_assert(2 * (smem + 1024) <= 227 * 1024, "stem+e12: two CTAs per SM");
     EVFLY_SMEM_ATTR(smem, k_tc_stem_e12);
     const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    const int grid = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
     k_tc_stem_e12<<<grid, 384, smem, (cudaStream_t)stream>>>(mw, p, sa);
     EVFLY_LAUNCHED();
     return EVFLY_OK;

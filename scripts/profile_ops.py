@@ -19,6 +19,7 @@ torch.cuda.synchronize()
 lib = _lib.load()
 records = collections.defaultdict(list)
 shapes = collections.defaultdict(list)
+halo_shapes = collections.defaultdict(list)
 order = []
 orig = {}
 for fn in _lib.SIGNATURES:
@@ -35,6 +36,10 @@ for fn in _lib.SIGNATURES:
             if fn == "evfly_tc_conv_bf16":       # per-shape breakdown of the GEMM family
                 st = a[0]._obj if hasattr(a[0], "_obj") else a[0].contents
                 shapes[(st.M_rows, st.Cin, st.n_rows, st.taps, st.convt, st.Hp, st.Wp)].append((e0, e1))
+            if fn in ("evfly_tc_conv3x3_halo_bf16", "evfly_tc_conv3x3_halo_pool_bf16", "evfly_tc_conv3x3_halo_out1_bf16"):
+                off = {"evfly_tc_conv3x3_halo_bf16": 4, "evfly_tc_conv3x3_halo_pool_bf16": 5, "evfly_tc_conv3x3_halo_out1_bf16": 6}[fn]
+                N, Hp, Wp, vh, vw, Cin, Cout = a[off:off + 7]      # (N, Hp, Wp, vh, vw, Cin, Cout) follow the pointers
+                halo_shapes[(fn.replace("evfly_tc_conv3x3_", ""), N, vh, vw, Cin, Cout)].append((e0, e1))
             return rc
         return wrapped
     setattr(lib, fn, make(fn, f))
@@ -53,6 +58,13 @@ for k, v in sorted(shapes.items(), key=lambda kv: -sum(x.elapsed_time(y) for x, 
     ms = sum(x.elapsed_time(y) for x, y in v)
     M, Cin, n_rows, taps = k[0], k[1], k[2], k[3]
     tf = 2.0 * M * Cin * taps * n_rows * len(v) / ms / 1e9
+    print(f"{ms:8.3f} ms {len(v):3d} calls {tf:7.1f} TFLOP/s  {k}")
+
+print("halo family by shape (entry, N, valid_h, valid_w, Cin, Cout):")
+for k, v in sorted(halo_shapes.items(), key=lambda kv: -sum(x.elapsed_time(y) for x, y in kv[1])):
+    ms = sum(x.elapsed_time(y) for x, y in v)
+    _, N, vh, vw, Cin, Cout = k
+    tf = 2.0 * N * (vh - 2) * (vw - 2) * Cin * 9 * Cout * len(v) / ms / 1e9
     print(f"{ms:8.3f} ms {len(v):3d} calls {tf:7.1f} TFLOP/s  {k}")
 
 if "--each" in sys.argv:
