@@ -77,6 +77,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same MMA issued from CONVERGENT code under a per-lane predicate (elected != 0 in exactly one lane). Inside an
+// `if (elect_one())` region the compiler keeps the descriptors in vector registers and moves every one of them to the uniform
+// file before its UTCHMMA (two R2UR per operand: ~26 clk of issue per MMA, more than an N <= 32 MMA takes to execute); in
+// convergent code warp-uniform descriptors stay in uniform registers.
+__device__ __forceinline__ void umma_bf16_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 e, %5, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t elected) {
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        "setp.ne.b32 e, %1, 0;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(elected)
+        : "memory");
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

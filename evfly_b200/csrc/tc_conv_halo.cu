@@ -309,37 +309,35 @@ k_tc_conv3x3_halo(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        // The whole warp walks the tile loop convergently and ONE elected lane issues. The descriptors of a tile differ
-        // from the stage's base descriptor only in the start-address field (bits [0,14), units of 16 B), by constants
-        // known at compile time, so an MMA costs one 64-bit add per operand. (Issuing from `lane == 0` with the
-        // descriptors rebuilt per MMA took ~75 clk per instruction; the tensor pipe needs ~40 at N <= 32,
-        // profiles/r1_microbench_mma_rate.json.)
+        // The whole warp walks the tile loop convergently and ONE elected lane issues, by predicate (umma_bf16_pred): the
+        // descriptors of a tile differ from the stage's base descriptor only in the start-address field (bits [0,14), units
+        // of 16 B) by compile-time constants and stay in uniform registers. (Issuing from `lane == 0` with the descriptors
+        // rebuilt per MMA took ~75 clk per instruction, from an `if (elect_one())` region ~26 clk of R2UR moves per MMA; the
+        // tensor pipe needs ~40 at N <= 32, profiles/r1_microbench_mma_rate.json.)
         constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
         mbar_wait(w_bar, 0);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         const uint64_t dw0 = make_smem_desc(smem_u32(s_w), Cfg::SBO_B, Cfg::LAYOUT);
         const uint64_t dh0 = make_smem_desc(smem_u32(s_halo), Cfg::SBO_A, Cfg::LAYOUT);
+        const uint32_t elected = elect_one() ? 1u : 0u;      // one lane issues every MMA and commit of this CTA (umma_bf16_pred)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * COUT);
             const uint64_t da0 = dh0 + (uint64_t)(stage * (Cfg::HALO_BYTES >> 4));
-            if (elect_one()) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                    for (int k = 0; k < CIN / 16; ++k) {
-                        const uint64_t da = da0 + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * Cfg::ROW_B + k * 32) >> 4);
-                        const uint64_t db = dw0 + (uint64_t)((tap * Cfg::W_TAP_BYTES + k * 32) >> 4);
-                        umma_bf16(tmem_d, da, db, idesc, (tap | k) != 0);
-                    }
+                for (int k = 0; k < CIN / 16; ++k) {
+                    const uint64_t da = da0 + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * Cfg::ROW_B + k * 32) >> 4);
+                    const uint64_t db = dw0 + (uint64_t)((tap * Cfg::W_TAP_BYTES + k * 32) >> 4);
+                    umma_bf16_pred(tmem_d, da, db, idesc, (tap | k) != 0, elected);
                 }
-                umma_commit(&empty_bar[stage]);
-                umma_commit(&tfull_bar[acc]);
             }
-            __syncwarp();
+            umma_commit_pred(&empty_bar[stage], elected);
+            umma_commit_pred(&tfull_bar[acc], elected);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
@@ -460,6 +458,7 @@ k_tc_conv3x3_halo_ws(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const uint64_t db_base = make_smem_desc(smem_u32(s_b), Cfg::SBO_B, kLayoutSw128);
         int slot = 0, acc = 0, it = 0;
         uint32_t b_phase = 0, acc_phase = 0;
+        const uint32_t elected = elect_one() ? 1u : 0u;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -474,22 +473,16 @@ k_tc_conv3x3_halo_ws(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     mbar_wait(&b_full[slot], b_phase);
                     tc_fence_after();
                     const uint64_t db_s = db_base + (uint64_t)((slot * Cfg::B_BLOCK) >> 4);
-                    if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem_d, da_c + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * 128 + k * 32) >> 4), db_s + (uint64_t)(k * 2), idesc,
-                                      (chunk | tap | k) != 0);
-                        umma_commit(&b_empty[slot]);
-                    }
-                    __syncwarp();
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_pred(tmem_d, da_c + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * 128 + k * 32) >> 4), db_s + (uint64_t)(k * 2), idesc,
+                                       (chunk | tap | k) != 0, elected);
+                    umma_commit_pred(&b_empty[slot], elected);
                     if (++slot == Cfg::NB) { slot = 0; b_phase ^= 1; }
                 }
             }
-            if (elect_one()) {
-                umma_commit(&a_empty[buf]);
-                umma_commit(&tfull_bar[acc]);
-            }
-            __syncwarp();
+            umma_commit_pred(&a_empty[buf], elected);
+            umma_commit_pred(&tfull_bar[acc], elected);
             if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
@@ -702,26 +695,24 @@ k_tc_stem_e12(const __grid_constant__ CUtensorMap map_w, const HaloArgs p, const
         uint32_t phase = 0, acc_phase = 0;
         const uint64_t dw0 = make_smem_desc(smem_u32(s_w), Cfg::SBO_B, Cfg::LAYOUT);
         const uint64_t dh0 = make_smem_desc(smem_u32(s_halo), Cfg::SBO_A, Cfg::LAYOUT);
+        const uint32_t elected = elect_one() ? 1u : 0u;      // one lane issues every MMA and commit of this CTA
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
             const uint64_t da0 = dh0 + (uint64_t)(stage * (Cfg::HALO_BYTES >> 4));
-            if (elect_one()) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint64_t da = da0 + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * Cfg::ROW_B + k * 32) >> 4);
-                        const uint64_t db = dw0 + (uint64_t)((tap * Cfg::W_TAP_BYTES + k * 32) >> 4);
-                        umma_bf16(tmem_d, da, db, idesc, (tap | k) != 0);
-                    }
+                for (int k = 0; k < 2; ++k) {
+                    const uint64_t da = da0 + (uint64_t)((((tap / 3) * 10 + (tap % 3)) * Cfg::ROW_B + k * 32) >> 4);
+                    const uint64_t db = dw0 + (uint64_t)((tap * Cfg::W_TAP_BYTES + k * 32) >> 4);
+                    umma_bf16_pred(tmem_d, da, db, idesc, (tap | k) != 0, elected);
                 }
-                umma_commit(&empty_bar[stage]);
-                umma_commit(&tfull_bar[acc]);
             }
-            __syncwarp();
+            umma_commit_pred(&empty_bar[stage], elected);
+            umma_commit_pred(&tfull_bar[acc], elected);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
         }

@@ -19,21 +19,14 @@ def timeit(fn, reps=5):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 
-names = {0: "baseline", 9: "trivial producer", 32: "trivial epilogue", 4: "1 MMA", 41: "trivial producer + trivial epilogue (MMA only)",
-         36: "1 MMA + trivial epilogue (producer only)", 13: "trivial producer + 1 MMA (epilogue only)",
-         173: "skeleton (1 MMA, all trivial)", 429: "skeleton, stage freed by a plain arrive (one commit per tile)",
-         685: "skeleton, epilogue arrives without tmem_ld", 941: "skeleton, one commit, no tmem_ld"}
+os.environ["EVFLY_STEM_DBG"] = "0"
 ref_out, ref_pool = tc.stem_e12_pool(mask, w1, b1, w2, b2)
-for two in (0, 1):
-    if two: os.environ["EVFLY_STEM_2CTA"] = "1"
-    else: os.environ.pop("EVFLY_STEM_2CTA", None)
-    os.environ["EVFLY_STEM_DBG"] = "0"
+names = {0: "try_wait (default)", 256: "test_wait spin", 512: "try_wait hint 32 ns", 768: "try_wait hint 256 ns", 1024: "try_wait hint 2000 ns"}
+for d, nm in names.items():
+    os.environ["EVFLY_STEM_DBG"] = str(d)
+    ms = timeit(lambda: tc.stem_e12_pool(mask, w1, b1, w2, b2))
     o, pl = tc.stem_e12_pool(mask, w1, b1, w2, b2)
-    print(f"stem_e12 N={N} ctas_per_sm={1 + two} equal_to_1cta: {torch.equal(o.data, ref_out.data)} {torch.equal(pl.data, ref_pool.data)}")
-    for d, nm in names.items():
-        os.environ["EVFLY_STEM_DBG"] = str(d)
-        ms = timeit(lambda: tc.stem_e12_pool(mask, w1, b1, w2, b2))
-        print(f"  dbg={d:4d} {ms:8.3f} ms  {nm}", flush=True)
+    print(f"  dbg={d:4d} {ms:8.3f} ms  {nm}  equal: {torch.equal(o.data, ref_out.data)} {torch.equal(pl.data, ref_pool.data)}", flush=True)
 os.environ["EVFLY_STEM_DBG"] = "0"
 os.environ.pop("EVFLY_STEM_2CTA", None)
 sys.exit(0)
