@@ -99,6 +99,7 @@ class TcConvArgs(C.Structure):
 SIGNATURES.update({
     "evfly_tc_conv_bf16": (_i32, [C.POINTER(TcConvArgs), _vp]),
     "evfly_convlstm_scan_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "evfly_convlstm_scan_fused_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
     "evfly_stem_conv3x3_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "evfly_stem_conv3x3_fma_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "evfly_maxpool2x2_nhwc_bf16": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -183,6 +184,9 @@ def load() -> C.CDLL:
         raise EvflyError("libevfly_b200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib
+
+
+ERR_UNSUPPORTED = -4      # EVFLY_ERR_UNSUPPORTED (include/evfly_b200.h)
 
 
 def check(rc: int, what: str = "") -> None:

@@ -247,7 +247,6 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
     float* cst = (float*)ws.take(P * Ch * 4);
     void* sync = ws.take(256);
     EVFLY_REQUIRE(ws.ok, "unet_forward: workspace exhausted (internal sizing error)");
-    RC(gemm_f32out(ye[4], (int64_t)T * P, Ch, wts->lstm_wx, nullptr, 4 * Ch, gx, stream));
     if (d_h0) {
         RC(evfly_nchw_f32_to_nhwc_bf16(d_h0, h_all, n_traj, Ch, vh5, vw5, Hp5, Wp5, stream));
         k_state_nchw_to_grid<<<stream_grid(P * Ch, 256, 8), 256, 0, st>>>(d_c0, cst, n_traj, Ch, vh5, vw5, Hp5, Wp5);
@@ -256,7 +255,15 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
         EVFLY_CUDA(cudaMemsetAsync(h_all, 0, P * Ch * 2, st));
         EVFLY_CUDA(cudaMemsetAsync(cst, 0, P * Ch * 4, st));
     }
-    RC(evfly_convlstm_scan_bf16(h_all, wts->lstm_wh, gx, cst, T, P, Ch, sync, stream));
+    {   // x-gates inside the persistent step kernel; where that grid cannot be co-resident: the x-gate GEMM + the per-step scan
+        const int rc_scan = evfly_convlstm_scan_fused_bf16(ye[4], wts->lstm_wx, h_all, wts->lstm_wh, cst, T, P, Ch, Ch, sync, stream);
+        if (rc_scan == EVFLY_ERR_UNSUPPORTED) {
+            RC(gemm_f32out(ye[4], (int64_t)T * P, Ch, wts->lstm_wx, nullptr, 4 * Ch, gx, stream));
+            RC(evfly_convlstm_scan_bf16(h_all, wts->lstm_wh, gx, cst, T, P, Ch, sync, stream));
+        } else {
+            RC(rc_scan);
+        }
+    }
     if (d_hT) RC(evfly_nhwc_to_nchw_f32(h_all + (int64_t)T * P * Ch, 0, d_hT, n_traj, Ch, vh5, vw5, Hp5, Wp5, stream));
     if (d_cT) {
         k_state_grid_to_nchw<<<stream_grid((int64_t)n_traj * Ch * vh5 * vw5, 256, 8), 256, 0, st>>>(cst, d_cT, n_traj, Ch, vh5, vw5, Hp5, Wp5);

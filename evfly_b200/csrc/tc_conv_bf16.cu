@@ -24,10 +24,6 @@
 
 namespace evfly {
 
-// sigmoid / tanh on the fast exponential (2 ulp __expf + approximate reciprocal): ~1e-6 absolute, far below the
-// bf16 rounding of h; libdevice tanhf costs ~10x more and made the fused ConvLSTM epilogue the bottleneck
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // ---------------------------------------------------------------------------------------
 struct TcArgs {
@@ -209,6 +205,64 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long mt = tile / n_tiles;
             const int nt = (int)(tile - mt * n_tiles);
             const long long m = mt * Cfg::BM + ew * 32 + lane;
+            if (p.lstm_c && res_step) {
+                // ===== ConvLSTM step with precomputed x-gates (the scan): the fp32 x-gates and c of the NEXT 32-column chunk are
+                // fetched while the current one is computed, and chunk 0 before the accumulator is even complete -- with the
+                // loads inside the chunk loop every chunk waited ~2 us for L2 and the epilogue was 21 of the 32 us of a step
+                // (profiles/r2_scan_timeline.txt). Arithmetic and its order are those of the generic path below (bit-identical).
+                const bool row_ok = m < p.M_rows;
+                const int Ch = p.n_rows >> 2;
+                const long long mc = row_ok ? m : 0;                       // masked rows read row 0 (never stored)
+                const float* rrow = res_step + mc * (long long)p.n_rows + nt * TN;
+                float* crow = p.lstm_c + mc * (long long)Ch + ((nt * TN) >> 2);
+                float4 nres[8], nc[2];
+                auto fetch = [&](int c0) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) nres[q] = *reinterpret_cast<const float4*>(rrow + c0 + 4 * q);
+                    nc[0] = *reinterpret_cast<const float4*>(crow + (c0 >> 2));
+                    nc[1] = *reinterpret_cast<const float4*>(crow + (c0 >> 2) + 4);
+                };
+                fetch(0);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 32) {
+                    float v[32];
+                    float cin[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { v[4 * q] = nres[q].x; v[4 * q + 1] = nres[q].y; v[4 * q + 2] = nres[q].z; v[4 * q + 3] = nres[q].w; }
+                    cin[0] = nc[0].x; cin[1] = nc[0].y; cin[2] = nc[0].z; cin[3] = nc[0].w; cin[4] = nc[1].x; cin[5] = nc[1].y; cin[6] = nc[1].z; cin[7] = nc[1].w;
+                    if (c0 + 32 < TN) fetch(c0 + 32);
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN + c0), r);
+                    tmem_ld_wait();
+                    const float* sb = s_bias + nt * TN + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(r[j]) + sb[j]) + v[j];
+                    float cn[8], hn[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float ig = fast_sigmoid(v[4 * q]), fg = fast_sigmoid(v[4 * q + 1]), og = fast_sigmoid(v[4 * q + 2]);
+                        cn[q] = fg * cin[q] + ig * fast_tanh(v[4 * q + 3]);
+                        hn[q] = og * fast_tanh(cn[q]);
+                    }
+                    if (row_ok) {
+                        float* cp = crow + (c0 >> 2);
+                        *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                        *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(hn[0], hn[1]), t1 = __floats2bfloat162_rn(hn[2], hn[3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(hn[4], hn[5]), t3 = __floats2bfloat162_rn(hn[6], hn[7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(lstm_h_step + m * (long long)Ch + ((nt * TN + c0) >> 2)) = pk;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                continue;
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             // destination pixel of this row
@@ -423,8 +477,8 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] (cols contiguous, row pitch ld elements), box [box_rows x box_cols]
-static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
-                       uint32_t box_cols) {
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                uint32_t box_cols) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");

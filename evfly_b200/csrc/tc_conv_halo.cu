@@ -85,27 +85,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// two fp32 -> one packed bf16x2 (lo = first channel), round-to-nearest-even; the .relu form clamps negatives to +0 first and
-// keeps NaN (as torch's relu does)
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint4 max4_bf16x2(const uint4& a, const uint4& b) {
-    return make_uint4(max_bf16x2(a.x, b.x), max_bf16x2(a.y, b.y), max_bf16x2(a.z, b.z), max_bf16x2(a.w, b.w));
-}
-
 // Position of a role in its strided walk over the tiles (tile = n * tiles_per_img + rem) without a division per tile:
 // the stride is split once into whole images and a remainder.
 struct TileWalk {

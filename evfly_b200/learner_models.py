@@ -494,8 +494,6 @@ class OrigUNet(PackedModule):
         cur = g
         for li, (wx, wh) in enumerate(Wl):
             Ch = wh.shape[1]
-            gx = torch.empty((T * P, 4 * Ch), dtype=torch.float32, device=dev)
-            tc.gemm(cur.data.view(T * P, cur.C), wx, None, out_f32=gx)
             c = torch.zeros((P, Ch), dtype=torch.float32, device=dev)
             h_all = torch.empty((T + 1, P, Ch), dtype=tc.BF16, device=dev)      # block 0 = h_0, block t+1 = h_t
             if state is not None:
@@ -504,7 +502,10 @@ class OrigUNet(PackedModule):
                 ops.map4d(cs.permute(0, 2, 3, 1), c.view(n_traj, Hp, Wp, Ch)[:, :g.vh, :g.vw])
             else:
                 h_all[0].zero_()
-            tc.convlstm_scan(h_all, wh, gx, c, T, P, Ch)     # T fused step kernels enqueued from C++
+            if not tc.convlstm_scan_fused(cur.data.view(T * P, cur.C), wx, h_all, wh, c, T, P, Ch):    # x-gates inside the step
+                gx = torch.empty((T * P, 4 * Ch), dtype=torch.float32, device=dev)
+                tc.gemm(cur.data.view(T * P, cur.C), wx, None, out_f32=gx)
+                tc.convlstm_scan(h_all, wh, gx, c, T, P, Ch)     # T fused step kernels enqueued from C++
             out = tc.Grid(h_all[1:].view(T * n_traj, Hp, Wp, Ch), g.vh, g.vw)
             h_last = tc.grid_to_nchw(h_all[T].view(n_traj, Hp, Wp, Ch), g.vh, g.vw)
             c_last = torch.empty((n_traj, Ch, g.vh, g.vw), dtype=torch.float32, device=dev)

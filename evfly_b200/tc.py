@@ -17,6 +17,7 @@ BF16 = torch.bfloat16
 USE_HALO = True      # small-channel 3x3 convs through the halo-reuse kernel
 FUSE_POOL = True     # MaxPool2d(2) in the epilogue of the halo-reuse kernel
 PERSISTENT_SCAN = True   # ConvLSTM recurrence as one persistent launch with a grid barrier per step
+FUSED_SCAN = True        # ... with the x half of the gate conv inside the step (no fp32 x-gate tensor); needs PERSISTENT_SCAN
 
 
 @dataclass
@@ -59,6 +60,15 @@ def pack_convt2x2_weight(w: torch.Tensor) -> torch.Tensor:
 
 def _call_scan(*args):
     _lib.check(_lib.load().evfly_convlstm_scan_bf16(*args, _lib.stream_ptr()), "evfly_convlstm_scan_bf16")
+
+
+def _call_scan_fused(*args) -> bool:
+    """False when the device cannot keep the persistent grid co-resident (the caller then takes the two-kernel path)."""
+    rc = _lib.load().evfly_convlstm_scan_fused_bf16(*args, _lib.stream_ptr())
+    if rc == _lib.ERR_UNSUPPORTED:
+        return False
+    _lib.check(rc, "evfly_convlstm_scan_fused_bf16")
+    return True
 
 
 def _call_halo(*args):
@@ -177,6 +187,16 @@ def convlstm_scan(h_all, wh_packed, gx, c_f32, T, P, Ch):
     """h_all bf16 [(T+1), P, Ch] (block 0 = h_0), gx fp32 [T*P, 4Ch], c fp32 [P,Ch]: the whole recurrence in one call."""
     sync = torch.empty((1,), dtype=torch.int64, device=c_f32.device) if PERSISTENT_SCAN else None
     _call_scan(h_all.data_ptr(), wh_packed.data_ptr(), _lib.ptr(gx), _lib.ptr(c_f32), T, P, Ch, _lib.ptr(sync))
+
+
+def convlstm_scan_fused(x_rows, wx_packed, h_all, wh_packed, c_f32, T, P, Ch) -> bool:
+    """x_rows bf16 [T*P, Cx] (time-major), h_all bf16 [(T+1), P, Ch] (block 0 = h_0), c fp32 [P,Ch]: the whole recurrence,
+    x-gates included, in one persistent launch. Returns False if that launch is not possible here (nothing was run)."""
+    if not (PERSISTENT_SCAN and FUSED_SCAN) or T < 1 or x_rows.shape[1] % 64 or Ch % 64:
+        return False
+    sync = torch.empty((1,), dtype=torch.int64, device=c_f32.device)
+    return _call_scan_fused(x_rows.data_ptr(), wx_packed.data_ptr(), h_all.data_ptr(), wh_packed.data_ptr(), _lib.ptr(c_f32), T, P, x_rows.shape[1], Ch,
+                            _lib.ptr(sync))
 
 
 def conv_transpose2x2(g: Grid, w_packed, bias, out_data: torch.Tensor, out_c0: int):

@@ -442,6 +442,16 @@ int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream);
 int evfly_convlstm_scan_bf16(void* d_h_all, const void* d_wh, const float* d_gx, float* d_c, int T, int64_t P,
                              int Ch, void* d_sync, void* stream);
 
+/* The same recurrence with the x half of the gate convolution inside the step (evfly_b200/csrc/convlstm_scan.cu): d_x bf16
+ * [T*P, Cx] are the ConvLSTM inputs in time-major order (learner_models.py:544-546 feeds unet_e52's output), d_wx bf16
+ * [4*Ch, Cx] and d_wh bf16 [4*Ch, Ch] the two halves of the gate conv (rows n = 4*ch + gate, i,f,o,g). The x-gates never exist
+ * in memory: per step gates = x_t W_x^T + h_{t-1} W_h^T is accumulated in TMEM (K = Cx + Ch) and the x part of step t+1 runs
+ * while the grid waits for h_t. Always one persistent cooperative launch (d_sync: 8 bytes of device scratch); returns
+ * EVFLY_ERR_UNSUPPORTED when the device cannot keep the grid co-resident -- use the x-gate GEMM + evfly_convlstm_scan_bf16
+ * then. Results differ from that pair only by fp32 summation order (the x-gates are no longer rounded to fp32 in between). */
+int evfly_convlstm_scan_fused_bf16(const void* d_x, const void* d_wx, void* d_h_all, const void* d_wh, float* d_c, int T,
+                                   int64_t P, int Cx, int Ch, void* d_sync, void* stream);
+
 /* First UNet layer (learner_models.py OrigUNet unet_e11, Cin = 1 or 2): fp32 NCHW [N,Cin,H,W] -> 3x3 valid
  * conv + bias + ReLU -> bf16 NHWC [N,H,W,32] on the input's own grid (valid (H-2)x(W-2)).
  * w fp32 [32,Cin,3,3] (PyTorch layout), bias fp32 [32]. Runs on tcgen05: every thread builds the im2col row

@@ -1,0 +1,4 @@
+timeout 600 python -m pytest tests/test_tc_gpu.py -m gpu -x -q -k "scan" 2>&1 | tail -6
+timeout 300 python scripts/exp_scan_timeline.py 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_models_bf16_gpu.py tests/test_stage_abi_gpu.py tests/test_bench_shape_parity_gpu.py tests/test_trajectories_gpu.py -m gpu -x -q 2>&1 | tail -6
+timeout 300 python scripts/profile_ops.py trajectories > gpurun_out/r2_profile_ops_cfg4_i.txt 2>&1; head -12 gpurun_out/r2_profile_ops_cfg4_i.txt

@@ -270,6 +270,42 @@ def test_halo_conv_fused_maxpool_is_bit_identical_to_separate_pool(cuda_lib, N, 
     check_bf16(tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw), ref, "fused pool")
 
 
+@pytest.mark.parametrize("T,P,Cx,Ch", [(12, 204, 512, 512), (6, 3264, 512, 512), (9, 816, 256, 512), (3, 100, 64, 64), (5, 5000, 512, 512)])
+def test_fused_convlstm_scan(cuda_lib, T, P, Cx, Ch):
+    """convlstm.py:44-53 with the x half of the gate conv inside the persistent step kernel (csrc/convlstm_scan.cu): against the
+    fp64 recurrence on the bf16-rounded operands, and against the x-gate GEMM + scan pair it replaces (same math, the x-gates are
+    not rounded to fp32 in between). P = 3264 is the bench shape (two tiles on some CTAs), P = 5000 needs several rounds per step."""
+    wx = tc.pack_convlstm_gate_weight((rnd(4 * Ch, Cx, seed=1, scale=Cx ** -0.5)).cuda())
+    wh = tc.pack_convlstm_gate_weight((rnd(4 * Ch, Ch, seed=2, scale=Ch ** -0.5)).cuda())
+    x = (rnd(T * P, Cx, seed=3)).to(BF).cuda()
+    h0 = (rnd(P, Ch, seed=4) * 0.3).to(BF).cuda()
+    c0 = (rnd(P, Ch, seed=5) * 0.5).cuda()
+    h_all = torch.empty((T + 1, P, Ch), dtype=BF, device="cuda")
+    h_all[0].copy_(h0)
+    c = c0.clone()
+    assert tc.convlstm_scan_fused(x, wx, h_all, wh, c, T, P, Ch)
+    # the pair it replaces
+    h_ref = torch.empty_like(h_all)
+    h_ref[0].copy_(h0)
+    c_ref = c0.clone()
+    gx = torch.empty((T * P, 4 * Ch), device="cuda")
+    tc.gemm(x, wx, None, out_f32=gx)
+    tc.convlstm_scan(h_ref, wh, gx, c_ref, T, P, Ch)
+    torch.cuda.synchronize()
+    dh = (h_all.float() - h_ref.float()).abs().max().item()
+    assert dh <= 2 ** -6 and (c - c_ref).abs().max().item() <= 1e-3, (dh, (c - c_ref).abs().max().item())      # summation order + bf16 rounding flips of h
+    if T * P * Ch <= 12 * 816 * 512:
+        wxd, whd = wx.float().cpu().double(), wh.float().cpu().double()
+        h, cc = h0.float().cpu().double(), c0.cpu().double()
+        xd = x.float().cpu().double()
+        for t in range(T):
+            g = (xd[t * P:(t + 1) * P] @ wxd.t() + h @ whd.t()).view(P, Ch, 4)
+            cc = torch.sigmoid(g[..., 1]) * cc + torch.sigmoid(g[..., 0]) * torch.tanh(g[..., 3])
+            h = (torch.sigmoid(g[..., 2]) * torch.tanh(cc)).to(BF).double()
+        check_bf16(h_all[T], h, "fused scan h_T")
+        np.testing.assert_allclose(c.cpu().double().numpy(), cc.numpy(), rtol=0, atol=2e-2)
+
+
 @pytest.mark.parametrize("T,P,Ch", [(12, 204, 512), (7, 816, 512), (3, 100, 64)])
 def test_persistent_convlstm_scan_equals_per_step_launches(cuda_lib, T, P, Ch):
     wh = tc.pack_convlstm_gate_weight((rnd(4 * Ch, Ch, seed=1, scale=Ch ** -0.5)).cuda())
