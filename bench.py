@@ -237,7 +237,7 @@ class TrajectoryEvalWorkload:
     job's 2048 (sharded r::G over the ranks): events -> count frames + 5-bin voxel grids -> decode -> 97th-percentile
     scale/clip -> OrigUNet_w_VITFLY_ViTLSTM (deployed config, bf16 tensor-core path); the model advances the
     trajectories together (time-major frames), so the ConvLSTM / LSTM scans are 100 steps, N_TRAJ wide.
-    Events travel in the 8-byte wire format (evfly_event8): resident in HBM for `value`, from pinned host memory
+    Events travel in the 4-byte wire format (evfly_event4; the streams are on the sensor's 1 us grid): resident in HBM for `value`, from pinned host memory
     through TrajectoryFeeder for `e2e`."""
     H, W, B, N_EV = 260, 346, 5, 100_000
     T, N_TRAJ, N_DISTINCT = 100, 16, 4
@@ -251,7 +251,7 @@ class TrajectoryEvalWorkload:
     @classmethod
     def describe(cls):
         return (f"cfg4: per GPU {cls.N_TRAJ} trajectories x {cls.T} windows (260x346, 100k events each; slice of 2048 trajectories "
-                "sharded over ranks): 8-byte wire records -> count frames + 5-bin voxel -> prep -> UNet+ConvLSTM+ViT-LSTM forward, "
+                "sharded over ranks): 4-byte wire records (1 us timestamps, delta-coded) -> count frames + 5-bin voxel -> prep -> UNet+ConvLSTM+ViT-LSTM forward, "
                 "bf16 tensor-core path, per-trajectory recurrent state")
 
     @property
@@ -273,7 +273,9 @@ class TrajectoryEvalWorkload:
         self.pipe = PerceptionPipeline(self.model, sensor_hw=(self.H, self.W), model_hw=(self.H, self.W), num_bins=self.B)
         # N_DISTINCT seeded streams, laid out N_TRAJ / N_DISTINCT times (separate copies in memory: nothing is reused
         # between the copies, neither records in L2 nor results)
-        distinct = [synthetic_stream(7000 + 64 * rank + s, self.T, self.N_EV, self.H, self.W) for s in range(min(self.N_DISTINCT, self.N_TRAJ))]
+        # timestamps on the sensor's 1 us grid, 33.333 ms windows: representable in the 4-byte wire record (WireBatch picks it)
+        distinct = [synthetic_stream(7000 + 64 * rank + s, self.T, self.N_EV, self.H, self.W, dur_ns=33_333_000, grid_ns=1000)
+                    for s in range(min(self.N_DISTINCT, self.N_TRAJ))]
         self.streams = [distinct[s % len(distinct)] for s in range(self.N_TRAJ)]
         self.wire_host = WireBatch.from_streams(self.streams, device, pin=True)                 # pinned host records + device tables
         self.wire_dev = self.wire_host.on_device(self.wire_host.records.to(device))
@@ -286,7 +288,7 @@ class TrajectoryEvalWorkload:
         # (q/kv/final/mlp1/mlp2 = 54.0 MFLOP/frame of the 0.1106 G ViT-LSTM total) + decoder Linear 4.7 M
         self.tc_flops = W_ * (self.FLOP_UNET - self.FLOP_STEM + self.FLOP_CONVLSTM + 0.0587e9)
         self.step_flops = W_ * (self.FLOP_UNET + self.FLOP_CONVLSTM + self.FLOP_VIT)
-        self.acc_bytes = 8 * W_ * self.N_EV + W_ * self.H * self.W * 4 * (2 + self.B)
+        self.acc_bytes = self.wire_host.record_bytes * W_ * self.N_EV + W_ * self.H * self.W * 4 * (2 + self.B)
 
     def begin(self, n_steps: int):
         """Called by the timing harness before a run of n_steps consecutive step() calls."""
@@ -311,7 +313,7 @@ class TrajectoryEvalWorkload:
         Returns (wall seconds for `steps` steps, first copy included; achieved H2D GB/s while copying)."""
         from evfly_b200.pipeline import TrajectoryFeeder
         torch = self.torch
-        feeder = TrajectoryFeeder(self.pipe, self.wire_host.records.shape[0], self.windows_per_step, record_bytes=8)
+        feeder = TrajectoryFeeder(self.pipe, self.wire_host.records.shape[0], self.windows_per_step, record_bytes=self.wire_host.record_bytes)
         for _ in feeder.run([self.wire_host] * 2):      # warm-up
             pass
         torch.cuda.synchronize()
@@ -329,14 +331,15 @@ class TrajectoryEvalWorkload:
         from evfly_b200 import tc
         torch = self.torch
         self._ev = getattr(self, "_ev", [])
-        hooks = ("_call", "_call_halo", "_call_halo_pool", "_call_scan", "_call_stem_e12", "_call_halo_out1")       # every launcher of the tcgen05 conv/GEMM kernels
+        hooks = ("_call", "_call_halo", "_call_halo_pool", "_call_scan", "_call_scan_fused", "_call_stem_e12", "_call_halo_out1")       # every launcher of the tcgen05 conv/GEMM kernels
         orig = {h: getattr(tc, h) for h in hooks}
 
         def timed(fn):
             def wrapper(*a):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); fn(*a); e1.record()
+                e0.record(); r = fn(*a); e1.record()
                 self._ev.append((e0, e1))
+                return r
             return wrapper
         for h in hooks:
             setattr(tc, h, timed(orig[h]))
@@ -393,7 +396,7 @@ class TrajectoryEvalWorkload:
         ach = self.tc_flops / (tc_ms / n_steps / 1e3) / 1e12
         acc_ms = sum(a.elapsed_time(b) for a, b in self._acc_ev) / n_steps
         self._extra = {"rooflines_other": [{
-            "bound": "hbm", "kernel": "accumulate_windows_ev8 (k_chunk_plan + k_chunk_sort + k_band_accumulate) + k_counts_normalise (decode + crop + quantile + clip)",
+            "bound": "hbm", "kernel": "accumulate_windows_ev4 (k_chunk_plan + k_chunk_sort + k_band_accumulate) + k_counts_normalise (decode + crop + quantile + clip)",
             "achieved": self.acc_bytes / (acc_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": self.acc_bytes / (acc_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": self.acc_bytes, "ms": acc_ms,
             "traffic": load_traffic("accumulate_cfg4")}],
@@ -552,7 +555,7 @@ class PipelineWorkload(TrajectoryEvalWorkload):
 
     @classmethod
     def describe(cls):
-        return ("cfg3: per GPU 1 trajectory x 256 windows (260x346, 100k events each) = one 256-step sequence: 8-byte wire records -> "
+        return ("cfg3: per GPU 1 trajectory x 256 windows (260x346, 100k events each) = one 256-step sequence: 4-byte wire records -> "
                 "count frames + 5-bin voxel -> prep -> UNet+ConvLSTM+ViT-LSTM forward, bf16 tensor-core path")
 
 
@@ -735,7 +738,7 @@ def main():
             "roofline": wl.roofline(dom_s / max(2, min(args.steps, 5)), peaks),
             "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
                     "h2d_gbs_while_copying_min_over_ranks": h2d_gbs, "ratio_to_value": e2e_val / value,
-                    "limiter": "H2D of the event records (PCIe / host memory): wire records are 8 bytes per event" if e2e_val < 0.9 * value else "the device step (copies fully overlapped)"},
+                    "limiter": "H2D of the event records (PCIe / host memory)" if e2e_val < 0.9 * value else "the device step (copies fully overlapped)"},
             "gpu_launches": launches, "clocks": clocks, "numa": numa, "build": _build.build_state(),
         }
         if hasattr(wl, "step_flops"):

@@ -46,6 +46,8 @@ SIGNATURES = {
     "evfly_accumulate_sorted_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32]),
     "evfly_accumulate_windows_sorted": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "evfly_accumulate_windows_ev8": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "evfly_accumulate_windows_ev4": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "evfly_accumulate_chunk_events": (_i32, []),
     "evfly_decode_crop": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "evfly_difflog_events_f64": (_i32, [_vp, _vp, _i64, _f64, _i32, _f64, _f64, _vp, _vp, _vp]),
     "evfly_min_cutoff_f32": (_i32, [_vp, _i64, _f32, _vp]),

@@ -122,11 +122,14 @@ k_chunk_plan(const int64_t* __restrict__ win_offsets, int n_windows, int* __rest
 
 // ---- pass 1 -------------------------------------------------------------------------------
 // sorted record: word0 = x | (row inside the band) << 16 | polarity << 31 ; word1 = t - t0 of the window (u32)
-template <bool REC16>
+// REC = bytes per input record: 16 (evfly_event), 8 (evfly_event8) or 4 (evfly_event4: time as a 12-bit delta in microseconds to the
+// previous record of the window; chunk_base_us[c] = offset of the last record before chunk c from the window's first edge)
+template <int REC>
 __global__ void __launch_bounds__(kSortThreads, 2)
 k_chunk_sort(const void* __restrict__ records, const int64_t* __restrict__ win_offsets, const int64_t* __restrict__ win_t0,
              const int64_t* __restrict__ win_t1, int n_windows, unsigned H, unsigned W, unsigned rows, uint32_t magic, int bands,
-             const int* __restrict__ chunk_first, int max_chunks, uint2* __restrict__ sorted, int* __restrict__ table_t) {
+             const int* __restrict__ chunk_first, int max_chunks, uint2* __restrict__ sorted, int* __restrict__ table_t,
+             const uint32_t* __restrict__ chunk_base_us) {
     extern __shared__ __align__(16) uint2 s_sorted[];     // [kChunk]
     __shared__ int s_hist[kMaxBands + 1];
     __shared__ int s_warp[kSortThreads / 32];
@@ -152,7 +155,7 @@ k_chunk_sort(const void* __restrict__ records, const int64_t* __restrict__ win_o
     const uint64_t len = live ? (uint64_t)(t1 - t0) : 0ull;
 
     uint32_t w0[kEPT], w1[kEPT], key[kEPT];     // key = band << 16 | rank (rank < 8192), 0xffffffff = dropped
-    if (REC16) {
+    if (REC == 16) {
         uint4 r[kEPT];
 #pragma unroll
         for (int u = 0; u < kEPT; ++u) {
@@ -169,6 +172,65 @@ k_chunk_sort(const void* __restrict__ records, const int64_t* __restrict__ win_o
             w0[u] = x | (pol << 31);
             w1[u] = (uint32_t)dt;
         }
+    } else if (REC == 4) {
+        // coalesced 4-byte loads, then the running time of the chunk: the deltas go through shared memory (the buffer of the sorted
+        // records is still free) so that every thread sums 16 CONSECUTIVE records, one block scan over the thread totals adds the
+        // rest, and the absolute offsets come back the same way
+        uint32_t r[kEPT];
+#pragma unroll
+        for (int u = 0; u < kEPT; ++u) {
+            const int k = u * kSortThreads + threadIdx.x;
+            r[u] = k < n_here ? __ldg(reinterpret_cast<const uint32_t*>(records) + ebeg + k) : 0x000fffffu;       // skip record, delta 0
+        }
+        uint32_t* s_dt = reinterpret_cast<uint32_t*>(s_sorted);                // [kChunk]
+#pragma unroll
+        for (int u = 0; u < kEPT; ++u) s_dt[u * kSortThreads + threadIdx.x] = r[u] >> 20;
+        __syncthreads();
+        {
+            uint32_t loc[kEPT];
+            const uint4* src = reinterpret_cast<const uint4*>(s_dt + threadIdx.x * kEPT);
+            uint32_t run = 0;
+#pragma unroll
+            for (int q = 0; q < kEPT / 4; ++q) {
+                const uint4 v = src[q];
+                run += v.x; loc[4 * q] = run; run += v.y; loc[4 * q + 1] = run; run += v.z; loc[4 * q + 2] = run; run += v.w; loc[4 * q + 3] = run;
+            }
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            uint32_t incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) s_warp[warp] = (int)incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t x = lane < kSortThreads / 32 ? (uint32_t)s_warp[lane] : 0u;
+                uint32_t ix = x;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, ix, d);
+                    if (lane >= d) ix += t;
+                }
+                if (lane < kSortThreads / 32) s_warp[lane] = (int)(ix - x);
+            }
+            __syncthreads();
+            const uint32_t before = chunk_base_us[c] + (uint32_t)s_warp[warp] + incl - run;
+            uint4* dst = reinterpret_cast<uint4*>(s_dt + threadIdx.x * kEPT);
+#pragma unroll
+            for (int q = 0; q < kEPT / 4; ++q) dst[q] = make_uint4(before + loc[4 * q], before + loc[4 * q + 1], before + loc[4 * q + 2], before + loc[4 * q + 3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kEPT; ++u) {
+            const unsigned x = r[u] & 1023u, y = (r[u] >> 10) & 511u, pol = (r[u] >> 19) & 1u;
+            const uint64_t dt = (uint64_t)s_dt[u * kSortThreads + threadIdx.x] * 1000ull;       // microseconds -> the nanoseconds of the other formats
+            const bool ok = x < W && y < H && dt < len && dt < (1ull << 32);
+            key[u] = ok ? y : 0xffffffffu;
+            w0[u] = x | (pol << 31);
+            w1[u] = (uint32_t)dt;
+        }
+        __syncthreads();      // s_dt is about to become s_sorted again (the ranking below does not touch it, the scatter does)
     } else {
         uint2 r[kEPT];
 #pragma unroll
@@ -415,9 +477,10 @@ static SortedWs carve_ws(void* ws, int64_t n, int n_windows, int bands) {
     return s;
 }
 
-template <bool REC16>
+template <int REC>
 static int run_sorted(const void* recs, int64_t n, const int64_t* offs, const int64_t* t0, const int64_t* t1, const int* out_slot, int slot_stride,
-                      int slot_offset, int n_windows, int H, int W, int B, int32_t* counts, float* voxel, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                      int slot_offset, int n_windows, int H, int W, int B, int32_t* counts, float* voxel, void* ws, int64_t ws_bytes, cudaStream_t st,
+                      const uint32_t* chunk_base_us = nullptr) {
     BandGeom g;
     EVFLY_REQUIRE(band_geometry(H, W, 2 + (voxel ? B : 0), n_windows, &g), "accumulate_windows (tiled): a row of %d pixels x %d planes does not fit shared memory", W, 2 + B);
     EVFLY_REQUIRE(n <= (1ll << 40), "accumulate_windows (tiled): too many events");
@@ -428,14 +491,14 @@ static int run_sorted(const void* recs, int64_t n, const int64_t* offs, const in
     const SortedWs s = carve_ws(ws, n, n_windows, g.bands);
     // per device: these attributes belong to the device's context, and setting them is cheap
     EVFLY_CUDA(cudaFuncSetAttribute(k_band_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    EVFLY_CUDA(cudaFuncSetAttribute(k_chunk_sort<REC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChunk * 8));
+    EVFLY_CUDA(cudaFuncSetAttribute(k_chunk_sort<REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChunk * 8));
     for (int w0 = 0; w0 < n_windows; w0 += 32768) {          // gridDim.y limit and chunk_first's int range
         const int nw = n_windows - w0 < 32768 ? n_windows - w0 : 32768;
         k_chunk_plan<<<1, 1024, 0, st>>>(offs + w0, nw, s.chunk_first);
         EVFLY_LAUNCHED();
         if (n > 0) {
-            k_chunk_sort<REC16><<<s.max_chunks, kSortThreads, kChunk * 8, st>>>(recs, offs + w0, t0 + w0, t1 + w0, nw, (unsigned)H, (unsigned)W, (unsigned)g.rows,
-                                                                       g.magic, g.bands, s.chunk_first, s.max_chunks, s.sorted, s.table_t);
+            k_chunk_sort<REC><<<s.max_chunks, kSortThreads, kChunk * 8, st>>>(recs, offs + w0, t0 + w0, t1 + w0, nw, (unsigned)H, (unsigned)W, (unsigned)g.rows,
+                                                                     g.magic, g.bands, s.chunk_first, s.max_chunks, s.sorted, s.table_t, chunk_base_us);
             EVFLY_LAUNCHED();
         }
         k_band_accumulate<<<dim3(g.bands, nw), 512, g.smem, st>>>(s.sorted, offs + w0, t0 + w0, t1 + w0, out_slot ? out_slot + w0 : nullptr, slot_stride,
@@ -476,7 +539,7 @@ extern "C" int evfly_accumulate_windows_sorted(const evfly_event* d_events, int6
         EVFLY_CUDA(cudaMemsetAsync(ranges, 0, sizeof(int64_t) * (T + 1), st));
     }
     const int64_t used = align_up(8ll * (T + 1), 256) + 256;
-    return run_sorted<true>(d_events, n, ranges, d_edges_ns, d_edges_ns + 1, nullptr, slot_stride, slot_offset, T, H, W, B, d_counts, d_voxel,
+    return run_sorted<16>(d_events, n, ranges, d_edges_ns, d_edges_ns + 1, nullptr, slot_stride, slot_offset, T, H, W, B, d_counts, d_voxel,
                             reinterpret_cast<uint8_t*>(d_ws) + used, ws_bytes - used, st);
 }
 
@@ -488,8 +551,23 @@ extern "C" int evfly_accumulate_windows_ev8(const evfly_event8* d_events, int64_
     EVFLY_REQUIRE(!d_voxel || (B >= 1 && B <= 64), "accumulate_windows_ev8: bad B=%d", B);
     EVFLY_REQUIRE((reinterpret_cast<uintptr_t>(d_events) & 7) == 0, "accumulate_windows_ev8: records must be 8-byte aligned");
     if (n_windows == 0) return EVFLY_OK;
-    return run_sorted<false>(d_events, n, d_win_offsets, d_win_t0, d_win_t1, d_out_slot, 1, 0, n_windows, H, W, B, d_counts, d_voxel, d_ws, ws_bytes,
+    return run_sorted<8>(d_events, n, d_win_offsets, d_win_t0, d_win_t1, d_out_slot, 1, 0, n_windows, H, W, B, d_counts, d_voxel, d_ws, ws_bytes,
                              (cudaStream_t)stream);
+}
+
+extern "C" int evfly_accumulate_chunk_events(void) { return kChunk; }
+
+extern "C" int evfly_accumulate_windows_ev4(const uint32_t* d_events, int64_t n, const int64_t* d_win_offsets, const int64_t* d_win_t0,
+                                            const int64_t* d_win_t1, const int32_t* d_out_slot, const uint32_t* d_chunk_base_us, int n_windows, int H,
+                                            int W, int B, int32_t* d_counts, float* d_voxel, void* d_ws, int64_t ws_bytes, void* stream) {
+    EVFLY_REQUIRE(n >= 0 && H > 0 && W > 0 && H <= 511 && W <= 1023 && n_windows >= 0 && n_windows <= 32768,
+                  "accumulate_windows_ev4: needs H <= 511, W <= 1023 (9 + 10 coordinate bits; (1023, 511) is the skip record) and at most 32768 windows");
+    EVFLY_REQUIRE(d_counts && d_win_offsets && d_win_t0 && d_win_t1 && d_chunk_base_us && d_ws && (d_events || n == 0), "accumulate_windows_ev4: null pointer");
+    EVFLY_REQUIRE(!d_voxel || (B >= 1 && B <= 64), "accumulate_windows_ev4: bad B=%d", B);
+    EVFLY_REQUIRE((reinterpret_cast<uintptr_t>(d_events) & 3) == 0, "accumulate_windows_ev4: records must be 4-byte aligned");
+    if (n_windows == 0) return EVFLY_OK;
+    return run_sorted<4>(d_events, n, d_win_offsets, d_win_t0, d_win_t1, d_out_slot, 1, 0, n_windows, H, W, B, d_counts, d_voxel, d_ws, ws_bytes,
+                         (cudaStream_t)stream, d_chunk_base_us);
 }
 
 extern "C" int evfly_pack_events_ev8(const evfly_event* d_events, int64_t n, const int64_t* d_edges_ns, int T, evfly_event8* d_out,

@@ -65,47 +65,122 @@ def pack_ev8_host(records: np.ndarray, edges_ns: np.ndarray):
     return out, offsets
 
 
-class WireBatch:
-    """A batch of n_traj trajectories of T windows each in the 8-byte wire format, ready for
-    L1.accumulate_windows_ev8 / PerceptionPipeline: records of all trajectories laid end to end (uint8 [n,8]; a
-    pinned HOST tensor for the feeder, a device tensor for the pipeline) plus the small per-window tables
-    (device int64 / int32): event index range, time range, and the output slot t*n_traj + s (time-major frames:
-    the model advances the trajectories together)."""
+# 4-byte wire record (include/evfly_b200.h evfly_event4): x [0,10) | y [10,19) | polarity [19] | delta [20,32) = microseconds since the
+# previous record of the same window (the window's first edge for its first record). (1023, 511) is a skip record that only
+# advances the time (gaps above 4095 us). Exact for streams on a 1 us grid (every DVS sensor's timestamps), H <= 511, W <= 1023.
+EV4_MAX_DELTA = 4095
+EV4_SKIP = 1023 | (511 << 10)
+CHUNK_EVENTS = 8192        # evfly_accumulate_chunk_events(): the device sorts windows in chunks of this many records
 
-    def __init__(self, records, win_offsets, win_t0, win_t1, out_slot, n_traj, T):
+
+def pack_ev4_host(records: np.ndarray, edges_ns: np.ndarray):
+    """Host-side packer of the 4-byte wire format: EVENT_DTYPE records of ONE time-sorted stream + window edges int64 [T+1] ->
+    (uint32 records [m], win_offsets int64 [T+1], chunk_base_us uint32 [sum_w ceil(n_w / CHUNK_EVENTS)]) or None when the stream
+    cannot be represented exactly (times or edges off the 1 us grid, not sorted). Events that can never count (outside the
+    windows, polarity >= 2) are dropped here; chunk_base_us[c] is the offset from the window's first edge of the last record
+    before chunk c of that window."""
+    t = records_time_ns(records)
+    edges_ns = np.asarray(edges_ns, dtype=np.int64)
+    T = len(edges_ns) - 1
+    if T < 1 or (edges_ns % 1000).any() or (np.diff(edges_ns) < 0).any() or (t.size > 1 and (np.diff(t) < 0).any()):
+        return None
+    offsets = np.searchsorted(t, edges_ns, side="left")
+    lo, hi = int(offsets[0]), int(offsets[-1])
+    r, tt = records[lo:hi], t[lo:hi]
+    w = np.clip(np.searchsorted(offsets, np.arange(lo, hi), side="right") - 1, 0, T - 1)
+    keep = (r["polarity"] < 2) & (r["x"] < 1023) & (r["y"] < 511)
+    r, tt, w = r[keep], tt[keep], w[keep]
+    dt = tt - edges_ns[w]
+    if (dt % 1000).any():
+        return None
+    dt_us = dt // 1000
+    first = np.ones(len(r), dtype=bool)
+    first[1:] = w[1:] != w[:-1]
+    prev = np.zeros(len(r), dtype=np.int64)
+    prev[1:] = dt_us[:-1]
+    prev[first] = 0
+    delta = dt_us - prev
+    n_esc = np.maximum(delta - 1, 0) // EV4_MAX_DELTA
+    rem = delta - n_esc * EV4_MAX_DELTA
+    per = 1 + n_esc
+    pos = np.cumsum(per) - 1
+    total = int(per.sum())
+    out = np.full(total, EV4_SKIP | (EV4_MAX_DELTA << 20), dtype=np.uint32)
+    out[pos] = (r["x"].astype(np.uint32) | (r["y"].astype(np.uint32) << 10) | (r["polarity"].astype(np.uint32) << 19) | (rem.astype(np.uint32) << 20))
+    cnt = np.bincount(w, weights=per, minlength=T).astype(np.int64)
+    offs = np.zeros(T + 1, dtype=np.int64)
+    np.cumsum(cnt, out=offs[1:])
+    cum = np.cumsum((out >> 20).astype(np.int64))                     # running time over the whole packed stream
+    bases = []
+    for k in range(T):
+        nchunk = -(-int(cnt[k]) // CHUNK_EVENTS)
+        if nchunk == 0:
+            continue
+        start = cum[offs[k] - 1] if offs[k] > 0 else 0
+        idx = offs[k] + np.arange(1, nchunk, dtype=np.int64) * CHUNK_EVENTS - 1
+        bases.append(np.concatenate([[0], cum[idx] - start]))
+    chunk_base = np.concatenate(bases).astype(np.uint32) if bases else np.zeros(0, dtype=np.uint32)
+    return out, offs, chunk_base
+
+
+class WireBatch:
+    """A batch of n_traj trajectories of T windows each in a wire format, ready for L1.accumulate_windows_wire /
+    PerceptionPipeline: records of all trajectories laid end to end (uint8 [n, record_bytes]; a pinned HOST tensor for
+    the feeder, a device tensor for the pipeline) plus the small per-window tables (device int64 / int32): event index
+    range, time range, and the output slot t*n_traj + s (time-major frames: the model advances the trajectories
+    together). record_bytes = 8: evfly_event8; 4: evfly_event4 (delta-coded time, chunk_base = the per-chunk time table)."""
+
+    def __init__(self, records, win_offsets, win_t0, win_t1, out_slot, n_traj, T, chunk_base=None):
         self.records, self.win_offsets, self.win_t0, self.win_t1, self.out_slot = records, win_offsets, win_t0, win_t1, out_slot
         self.n_traj, self.T = int(n_traj), int(T)
+        self.chunk_base = chunk_base
+        self.record_bytes = int(records.shape[1])
 
     @property
     def n_windows(self):
         return self.n_traj * self.T
 
     @staticmethod
-    def from_streams(streams, device, pin=True):
-        """streams: list of (EVENT_DTYPE records, edges int64 [T+1]) of equal T (host numpy). Packs on the host."""
+    def from_streams(streams, device, pin=True, fmt="auto"):
+        """streams: list of (EVENT_DTYPE records, edges int64 [T+1]) of equal T (host numpy). Packs on the host.
+        fmt: 8 = evfly_event8, 4 = evfly_event4 (raises if a stream is not on the 1 us grid), "auto" = 4 when every stream
+        can be represented exactly in it, else 8."""
         T = len(streams[0][1]) - 1
         assert all(len(e) - 1 == T for _, e in streams), "trajectories must have the same number of windows"
         n = len(streams)
-        recs, offs, t0, t1, base = [], [], [], [], 0
-        for r, e in streams:
-            r8, o = pack_ev8_host(r, e)
-            recs.append(r8)
+        packed4 = None
+        if fmt in ("auto", 4):
+            packed4 = [pack_ev4_host(r, e) for r, e in streams]
+            if any(p is None for p in packed4):
+                if fmt == 4:
+                    raise ValueError("a stream cannot be represented in the 4-byte wire format (times off the 1 us grid, or not sorted)")
+                packed4 = None
+        recs, offs, t0, t1, cb, base = [], [], [], [], [], 0
+        for i, (r, e) in enumerate(streams):
+            if packed4 is not None:
+                r_p, o, c = packed4[i]
+                cb.append(c)
+            else:
+                r_p, o = pack_ev8_host(r, e)
+            recs.append(r_p)
             # window (s,t) = [base + o[t], next start): records of a trajectory that lie outside its windows were made
-            # skip records by the packer, so a range may harmlessly include them
+            # skip records by the 8-byte packer (dropped by the 4-byte one), so a range may harmlessly include them
             offs.append(o[:-1] + base)
             t0.append(np.asarray(e[:-1], np.int64)); t1.append(np.asarray(e[1:], np.int64))
-            base += r8.shape[0]
+            base += r_p.shape[0]
         offs.append(np.array([base], dtype=np.int64))
-        host = torch.from_numpy(np.concatenate(recs).view(np.uint8).reshape(-1, 8))
+        rb = 4 if packed4 is not None else 8
+        host = torch.from_numpy(np.concatenate(recs).view(np.uint8).reshape(-1, rb))
         if pin:
             host = host.pin_memory()
         slot = (np.arange(T, dtype=np.int32)[None, :] * n + np.arange(n, dtype=np.int32)[:, None]).reshape(-1)
         dev = torch.device(device)
+        chunk_base = torch.from_numpy(np.concatenate(cb).view(np.int32)).to(dev) if packed4 is not None else None
         return WireBatch(host, torch.from_numpy(np.concatenate(offs)).to(dev), torch.from_numpy(np.concatenate(t0)).to(dev),
-                         torch.from_numpy(np.concatenate(t1)).to(dev), torch.from_numpy(slot).to(dev), n, T)
+                         torch.from_numpy(np.concatenate(t1)).to(dev), torch.from_numpy(slot).to(dev), n, T, chunk_base)
 
     def on_device(self, device_records):
-        return WireBatch(device_records, self.win_offsets, self.win_t0, self.win_t1, self.out_slot, self.n_traj, self.T)
+        return WireBatch(device_records, self.win_offsets, self.win_t0, self.win_t1, self.out_slot, self.n_traj, self.T, self.chunk_base)
 
 
 def to_device(records, device=None, pinned: torch.Tensor | None = None) -> torch.Tensor:
@@ -290,6 +365,32 @@ class L1:
                                                     _lib.ptr(out_slot), nw, H, W, 0 if B is None else B, _lib.ptr(counts), _lib.ptr(voxel),
                                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "evfly_accumulate_windows_ev8")
         return counts, voxel
+
+    @staticmethod
+    def accumulate_windows_ev4(records4, win_offsets, win_t0, win_t1, chunk_base, H, W, B=None, *, out_slot=None, n_slots=None, counts=None, voxel=None):
+        """4-byte wire records uint8 [n,4] + per-window tables + the per-chunk time table (pack_ev4_host) on the device -> as
+        accumulate_windows_ev8. Same frames as the 8-byte format of the same stream (counts bit-exact; identical event times)."""
+        lib = _lib.load()
+        dev = records4.device
+        nw = win_t0.shape[0]
+        n_slots = nw if n_slots is None else n_slots
+        if counts is None:
+            counts = torch.empty((n_slots, 2, H, W), dtype=torch.int32, device=dev)
+        if B is not None and voxel is None:
+            voxel = torch.empty((n_slots, B, H, W), dtype=torch.float32, device=dev)
+        ws = L1.sorted_workspace(records4.shape[0], nw, H, W, B, dev)
+        _lib.check(lib.evfly_accumulate_windows_ev4(_lib.ptr(records4), records4.shape[0], _lib.ptr(win_offsets), _lib.ptr(win_t0), _lib.ptr(win_t1),
+                                                    _lib.ptr(out_slot), _lib.ptr(chunk_base), nw, H, W, 0 if B is None else B, _lib.ptr(counts),
+                                                    _lib.ptr(voxel), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "evfly_accumulate_windows_ev4")
+        return counts, voxel
+
+    @staticmethod
+    def accumulate_windows_wire(wb, H, W, B=None, *, counts=None, voxel=None):
+        """A WireBatch (records on the device) in either wire format -> frames in its time-major slots."""
+        kw = dict(out_slot=wb.out_slot, n_slots=wb.n_traj * wb.T, counts=counts, voxel=voxel)
+        if wb.record_bytes == 4:
+            return L1.accumulate_windows_ev4(wb.records, wb.win_offsets, wb.win_t0, wb.win_t1, wb.chunk_base, H, W, B, **kw)
+        return L1.accumulate_windows_ev8(wb.records, wb.win_offsets, wb.win_t0, wb.win_t1, H, W, B, **kw)
 
     @staticmethod
     def accumulate_windows(records, edges_ns: torch.Tensor, H, W, B=None, *, sorted_by_time=True,

@@ -104,8 +104,7 @@ class PerceptionPipeline:
         """L1 + L2 for a WireBatch (8-byte wire records of n_traj trajectories x T windows, already on the device):
         one accumulation call for all windows, frames in time-major slots. Same returns as frames_from_trajectories."""
         n, T = wb.n_traj, wb.T
-        counts, voxel = L1.accumulate_windows_ev8(wb.records, wb.win_offsets, wb.win_t0, wb.win_t1, self.H, self.W,
-                                                  self.B if want_voxel else None, out_slot=wb.out_slot, n_slots=n * T)
+        counts, voxel = L1.accumulate_windows_wire(wb, self.H, self.W, self.B if want_voxel else None)
         frames = torch.empty((T * n, 1, self.h, self.w), dtype=torch.float32, device=self.dev)
         self._normalise(counts, frames)
         return (frames, counts.view(T, n, 2, self.H, self.W).transpose(0, 1),

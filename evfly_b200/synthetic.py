@@ -8,8 +8,8 @@ from .events import EVENT_DTYPE, NS, make_records
 
 
 def synthetic_window(seed: int, n_events: int, H: int, W: int, *, t0_ns: int = 0,
-                     dur_ns: int = 33_333_333, distribution: str = "uniform") -> np.ndarray:
-    """One window of events sorted by time.
+                     dur_ns: int = 33_333_333, distribution: str = "uniform", grid_ns: int = 1) -> np.ndarray:
+    """One window of events sorted by time. grid_ns: timestamp resolution (1000 = the 1 us grid of a DVS sensor).
 
     uniform   : x~U{0..W-1}, y~U{0..H-1}, p~Bern(.5), t sorted U[t0, t0+dur)   (cfg 1 / 2)
     clustered : 80 % of the events on 2 % of the pixels (edge-like hot spots)   (cfg 2)
@@ -28,15 +28,15 @@ def synthetic_window(seed: int, n_events: int, H: int, W: int, *, t0_ns: int = 0
     else:
         raise ValueError(distribution)
     p = rng.integers(0, 2, n_events, dtype=np.int64)
-    t = np.sort(rng.integers(0, dur_ns, n_events, dtype=np.int64)) + t0_ns
+    t = np.sort(rng.integers(0, dur_ns // grid_ns, n_events, dtype=np.int64)) * grid_ns + t0_ns
     return make_records(x, y, t, p)
 
 
 def synthetic_stream(seed: int, n_windows: int, events_per_window: int, H: int, W: int, *,
-                     dur_ns: int = 33_333_333, distribution: str = "uniform"):
+                     dur_ns: int = 33_333_333, distribution: str = "uniform", grid_ns: int = 1):
     """`n_windows` consecutive windows of one stream. Returns (records, edges_ns int64 [T+1])."""
     parts = [synthetic_window(seed * 100003 + w, events_per_window, H, W, t0_ns=w * dur_ns,
-                              dur_ns=dur_ns, distribution=distribution) for w in range(n_windows)]
+                              dur_ns=dur_ns, distribution=distribution, grid_ns=grid_ns) for w in range(n_windows)]
     edges = np.arange(n_windows + 1, dtype=np.int64) * dur_ns
     return np.concatenate(parts), edges
 

@@ -143,6 +143,21 @@ int evfly_accumulate_windows_ev8(const evfly_event8* d_events, int64_t n, const 
                                  int n_windows, int H, int W, int B, int32_t* d_counts, float* d_voxel, void* d_ws,
                                  int64_t ws_bytes, void* stream);
 
+/* The 4-byte wire record (uint32): x [0,10) | y [10,19) | polarity [19] | delta [20,32), delta = microseconds since the previous
+ * record of the same window (since the window's first edge for its first record); (x, y) = (1023, 511) is a skip record that
+ * only advances the time (gaps above 4095 us). It halves the host->device bytes of the 8-byte record again (at 8 GPUs per host
+ * the event records are what bounds the end-to-end rate) and is exact for streams on a 1 us grid -- the timestamps of every
+ * DVS sensor (evfly_ros / dvs_msgs carry ros::Time, filled from the sensor's microsecond counter). H <= 511, W <= 1023,
+ * n_windows <= 32768. The time of a record is a running sum, which the kernel forms per chunk of
+ * evfly_accumulate_chunk_events() records: d_chunk_base_us[c] is the offset (us) from the window's first edge of the last
+ * record before chunk c, chunks numbered window by window (window w has ceil(n_w / chunk) of them). The host packer that
+ * writes all of this is evfly_b200.events.pack_ev4_host. Frames are those of evfly_accumulate_windows_ev8 on the same stream. */
+int evfly_accumulate_chunk_events(void);
+int evfly_accumulate_windows_ev4(const uint32_t* d_events, int64_t n, const int64_t* d_win_offsets, const int64_t* d_win_t0,
+                                 const int64_t* d_win_t1, const int32_t* d_out_slot, const uint32_t* d_chunk_base_us,
+                                 int n_windows, int H, int W, int B, int32_t* d_counts, float* d_voxel, void* d_ws,
+                                 int64_t ws_bytes, void* stream);
+
 /* counts[pol][y][x] += #events, pol 0 = negative plane, 1 = positive plane; int32 [2,H,W].
  * Events with x >= W or y >= H (unsigned compare, node.cpp:31) or polarity >= 2 are ignored.
  * The caller zeroes d_counts (or keeps accumulating into it across calls, which is how the

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from evfly_b200 import _lib
-from evfly_b200.events import EVENT8_DTYPE, L1, WireBatch, make_records, pack_ev8_host, to_device
+from evfly_b200.events import EVENT8_DTYPE, L1, WireBatch, make_records, pack_ev4_host, pack_ev8_host, to_device
 from evfly_b200.synthetic import synthetic_stream, synthetic_window
 from oracle import ev_oracle as O
 
@@ -91,6 +91,52 @@ def test_wire_batch_time_major_slots(cuda_lib):
         c_ref, v_ref = O.windows(rec, edges, H, W, B=B)
         assert np.array_equal(counts.view(T, n, 2, H, W)[:, s].cpu().numpy(), c_ref)
         _check_voxel(vox.view(T, n, B, H, W)[:, s].cpu().numpy(), v_ref)
+
+
+@pytest.mark.parametrize("H,W,T,n_per,dur_us", [(260, 346, 6, 100_000, 33_333), (480, 640, 3, 40_000, 33_333), (260, 346, 5, 6, 33_333),
+                                                 (37, 53, 4, 9_000, 2_000), (260, 346, 2, 300, 2_000_000)])
+def test_4_byte_wire_format_equals_8_byte(cuda_lib, H, W, T, n_per, dur_us):
+    """evfly_event4 (delta-coded microsecond time, per-chunk base table): the same frames as evfly_event8 on the same stream --
+    counts bit for bit, voxel within the usual sum-order bound -- and as the oracle. 6 events per 33 ms window and 300 per 2 s
+    window force escape records (gaps above 4095 us); 100 k events span 13 chunks per window."""
+    rec, edges = synthetic_stream(5, T, n_per, H, W, dur_ns=dur_us * 1000, grid_ns=1000)
+    edges = edges.copy()
+    edges[0] += 7_000          # events before the first edge are dropped
+    packed = pack_ev4_host(rec, edges)
+    assert packed is not None
+    r4, offs4, cb = packed
+    if n_per <= 300:
+        assert ((r4 & 0x7FFFF) == (1023 | (511 << 10))).any()          # escape records are present
+    assert cb.shape[0] == sum(-(-int(n) // 8192) for n in np.diff(offs4))
+    d4 = torch.from_numpy(r4.view(np.uint8).reshape(-1, 4)).cuda()
+    t0, t1 = torch.from_numpy(edges[:-1].copy()).cuda(), torch.from_numpy(edges[1:].copy()).cuda()
+    B = 5
+    c4, v4 = L1.accumulate_windows_ev4(d4, torch.from_numpy(offs4).cuda(), t0, t1, torch.from_numpy(cb.view(np.int32)).cuda(), H, W, B)
+    r8, offs8 = pack_ev8_host(rec, edges)
+    d8 = torch.from_numpy(r8.view(np.uint8).reshape(-1, 8)).cuda()
+    c8, v8 = L1.accumulate_windows_ev8(d8, torch.from_numpy(offs8).cuda(), t0, t1, H, W, B)
+    assert torch.equal(c4, c8)
+    assert (v4 - v8).abs().max().item() <= 1e-4
+    c_ref, v_ref = O.windows(rec, edges, H, W, B=B)
+    assert np.array_equal(c4.cpu().numpy(), c_ref)
+    _check_voxel(v4.cpu().numpy(), v_ref)
+
+
+def test_wire_batch_picks_the_4_byte_format_when_exact(cuda_lib):
+    H, W, T, B, n = 260, 346, 4, 5, 3
+    on_grid = [synthetic_stream(60 + s, T, 30_000, H, W, dur_ns=33_333_000, grid_ns=1000) for s in range(n)]
+    wb = WireBatch.from_streams(on_grid, "cuda", pin=False)
+    assert wb.record_bytes == 4 and wb.chunk_base is not None
+    counts, vox = L1.accumulate_windows_wire(wb.on_device(wb.records.cuda()), H, W, B)
+    for s, (rec, edges) in enumerate(on_grid):
+        c_ref, v_ref = O.windows(rec, edges, H, W, B=B)
+        assert np.array_equal(counts.view(T, n, 2, H, W)[:, s].cpu().numpy(), c_ref)
+        _check_voxel(vox.view(T, n, B, H, W)[:, s].cpu().numpy(), v_ref)
+    off_grid = [synthetic_stream(60 + s, T, 30_000, H, W) for s in range(n)]        # nanosecond timestamps
+    wb8 = WireBatch.from_streams(off_grid, "cuda", pin=False)
+    assert wb8.record_bytes == 8 and wb8.chunk_base is None
+    with pytest.raises(ValueError):
+        WireBatch.from_streams(off_grid, "cuda", pin=False, fmt=4)
 
 
 def test_tiles_10M_events_one_window(cuda_lib):
