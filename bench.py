@@ -306,21 +306,22 @@ class TrajectoryEvalWorkload:
             self._next = self.pipe.prefetch_wire(self.wire_dev) if i + 1 < getattr(self, "_n_steps", 0) else None
             self.out = self.pipe.run_prefetched(cur)
 
-    def e2e_run(self, steps: int):
+    def e2e_run(self, steps: int, warmup: int = 3):
         """End to end through the public API (evfly_b200.pipeline.TrajectoryFeeder): every step's wire records start in
         pinned HOST memory, are copied to the device (copy stream, double-buffered so the copy of step i+1 overlaps the
         compute of step i), run through the pipeline, and the velocity commands are read back to the host.
-        Returns (wall seconds for `steps` steps, first copy included; achieved H2D GB/s while copying)."""
+        ONE continuous run of warmup + steps batches; the clock runs from the moment the last warm-up result is on the host
+        to the moment the last timed result is: `steps` copies, forwards and read-backs in the steady state of the feeder
+        (which works one batch ahead; a separate warm-up run would put the pipeline's fill -- one un-overlapped copy of
+        0.64 GB -- into a region of a handful of steps). Returns (wall seconds, achieved H2D GB/s while copying)."""
         from evfly_b200.pipeline import TrajectoryFeeder
         torch = self.torch
+        warmup = max(1, warmup)
         feeder = TrajectoryFeeder(self.pipe, self.wire_host.records.shape[0], self.windows_per_step, record_bytes=self.wire_host.record_bytes)
-        for _ in feeder.run([self.wire_host] * 2):      # warm-up
-            pass
-        torch.cuda.synchronize()
-        feeder.h2d_log.clear()
-        t0 = time.perf_counter()
-        for vel in feeder.run([self.wire_host] * steps):
-            pass
+        t0 = None
+        for k, vel in enumerate(feeder.run([self.wire_host] * (warmup + steps))):
+            if k == warmup - 1:
+                t0 = time.perf_counter()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         return dt, feeder.h2d_gbs()[0]
@@ -715,7 +716,7 @@ def main():
     h2d_gbs = None
     if hasattr(wl, "e2e_run"):
         barrier()
-        e2e_local, h2d_local = wl.e2e_run(e2e_steps)
+        e2e_local, h2d_local = wl.e2e_run(e2e_steps, args.warmup)
         t = torch.tensor([e2e_local, -h2d_local], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

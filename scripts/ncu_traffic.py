@@ -2,7 +2,7 @@
 
 On the GPU box (under gpurun; one GPU, never a multi-rank command):
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-        -k regex:'k_tc_|k_chunk|k_band|k_counts_norm|k_window' \
+        -k regex:'k_tc_|k_convlstm|k_chunk|k_band|k_counts_norm|k_window' \
         --csv --log-file gpurun_out/r2_traffic_cfg4.csv python scripts/ncu_traffic.py run cfg4
     ncu ... --log-file gpurun_out/r2_traffic_cfg2.csv python scripts/ncu_traffic.py run cfg2
 Here:
@@ -19,7 +19,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-TC = re.compile(r"k_tc_conv|k_tc_stem")
+TC = re.compile(r"k_tc_conv|k_tc_stem|k_convlstm_scan")
 ACC = re.compile(r"k_chunk_plan|k_chunk_sort|k_band_accumulate|k_window_ranges")
 NORM = re.compile(r"k_counts_normalise")
 
