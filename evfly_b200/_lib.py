@@ -119,12 +119,14 @@ SIGNATURES.update({
     "evfly_tc_conv3x3_same_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_shuffle_upsample_cat_bf16": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
     "evfly_tc_conv3x3_halo_pool_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_tc_conv3x3_halo_pool_rows_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_vit_ffn_image_bytes": (_i64, [_i32]),
     "evfly_vit_ffn_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "evfly_vit_attn_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "evfly_stem_patterns": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "evfly_form_patterns": (_i32, [_vp, _f32, _vp, _i32, _i32, _i32, _vp]),
     "evfly_tc_stem_e12_pool_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_tc_stem_e12_pool_rows_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_lstm_seq_smemw": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
 })
 

@@ -88,8 +88,9 @@ static inline bool halo_ok(int cin, int cout) {
 
 // 3x3 valid conv + bias + ReLU on the pitch grid (+ optional MaxPool2d(2) of the result), the dispatch of tc.conv3x3(_pool)
 static int conv3(const void* x, int N, int Hp, int Wp, int vh, int vw, int Cin, const void* w, const float* b, int Cout, void* out, void* pool,
-                 int Hp2, int Wp2, void* st) {
+                 int Hp2, int Wp2, void* st, int skip_OH = 0) {
     if (halo_ok(Cin, Cout)) {
+        if (pool && skip_OH > 0) return evfly_tc_conv3x3_halo_pool_rows_bf16(x, w, b, out, pool, N, Hp, Wp, vh, vw, Cin, Cout, 1, Hp2, Wp2, skip_OH, st);
         if (pool) return evfly_tc_conv3x3_halo_pool_bf16(x, w, b, out, pool, N, Hp, Wp, vh, vw, Cin, Cout, 1, Hp2, Wp2, st);
         return evfly_tc_conv3x3_halo_bf16(x, w, b, out, N, Hp, Wp, vh, vw, Cin, Cout, 1, st);
     }
@@ -226,7 +227,16 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
         RC(evfly_form_patterns(d_frames, cutoff, pat, N, H, W, stream));
         ye[0] = ws.take((int64_t)N * H * W * 32 * 2);
         void* pooled = ws.take((int64_t)N * g.Hp[1] * g.Wp[1] * 32 * 2);
-        RC(evfly_tc_stem_e12_pool_bf16(pat, wts->e11_w, wts->e11_b, wts->conv_w[0], wts->conv_b[0], ye[0], pooled, N, H, W, 1, g.Hp[1], g.Wp[1], stream));
+        // y_e1..y_e3 are only sampled by the decoder's bilinear skip: heights 2 * (valid height of that decoder level's input)
+        int skip_oh[4];
+        {
+            int vh = g.ev[4][0];
+            for (int el = 3; el >= 0; --el) {
+                skip_oh[el] = 2 * vh;
+                vh = 2 * vh - 4;
+            }
+        }
+        RC(evfly_tc_stem_e12_pool_rows_bf16(pat, wts->e11_w, wts->e11_b, wts->conv_w[0], wts->conv_b[0], ye[0], pooled, N, H, W, 1, g.Hp[1], g.Wp[1], skip_oh[0], stream));
         const void* x = pooled;
         for (int l = 1; l < 5; ++l) {
             const int Hp = g.Hp[l], Wp = g.Wp[l], Cin = kEncC[l], C = kEncC[l + 1];
@@ -235,7 +245,8 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
             ye[l] = ws.take(px * C * 2);
             void* nxt = l < 4 ? ws.take((int64_t)N * g.Hp[l + 1] * g.Wp[l + 1] * C * 2) : nullptr;
             RC(conv3(x, N, Hp, Wp, Hp, Wp, Cin, wts->conv_w[2 * l - 1], wts->conv_b[2 * l - 1], C, c1, nullptr, 0, 0, stream));
-            RC(conv3(c1, N, Hp, Wp, Hp - 2, Wp - 2, C, wts->conv_w[2 * l], wts->conv_b[2 * l], C, ye[l], nxt, l < 4 ? g.Hp[l + 1] : 0, l < 4 ? g.Wp[l + 1] : 0, stream));
+            RC(conv3(c1, N, Hp, Wp, Hp - 2, Wp - 2, C, wts->conv_w[2 * l], wts->conv_b[2 * l], C, ye[l], nxt, l < 4 ? g.Hp[l + 1] : 0, l < 4 ? g.Wp[l + 1] : 0, stream,
+                     l < 3 ? skip_oh[l] : 0));
             x = nxt;
         }
     }

@@ -42,7 +42,13 @@ struct HaloArgs {
     const float* w1;      // [COUT] (bf16-rounded values as fp32), or nullptr
     const float* b1;      // [1]
     float* out1;          // [N, Hp, Wp] fp32
+    // optional: `out` will only be sampled by evfly_resize_bilinear_nhwc_bf16 to a height of skip_OH (the decoder's interp skip,
+    // learner_models.py:512-519): bit r set = output row r is read by that resize; rows with a clear bit are not written
+    uint32_t row_mask[16];
+    int use_rows;
 };
+
+__device__ __forceinline__ bool row_wanted(const HaloArgs& p, int r) { return !p.use_rows || ((p.row_mask[r >> 5] >> (r & 31)) & 1u); }
 
 template <int CIN, int COUT>
 struct HaloCfg {
@@ -171,7 +177,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                     // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
                     sts128(my_row + (((uint32_t)((c0 >> 3) + q) ^ my_swz) << 4), val);
                 } else {
-                    if (ok) reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT + c0)[q] = val;
+                    if (ok && row_wanted(p, oh)) reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT + c0)[q] = val;
                     if (p.pool_out) {
                         // fused 2x2 max-pool: the partners of pixel (r, c) are lanes ^1 (column) and ^8 (row) of the same warp; the
                         // lane with even r and even c writes. max commutes with the (monotonic) bf16 rounding, so the result
@@ -213,7 +219,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
             for (int j = 0; j < kCP; ++j) {
                 const int id = j * 32 + lane, px = id / kCP, ch = id % kCP;
                 const int poh = ty * 16 + ew * 4 + (px >> 3), pow_ = tx * 8 + (px & 7);
-                if (poh < p.out_vh && pow_ < p.out_vw) {
+                if (poh < p.out_vh && pow_ < p.out_vw && row_wanted(p, poh)) {
                     const uint4 val = lds128(my_stage + px * (COUT * 2) + ((ch ^ (kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4));
                     *reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + poh) * p.Wp + pow_) * COUT + ch * 8) = val;
                 }
@@ -778,6 +784,26 @@ static int launch_halo_ws(const void* x, const void* w, const HaloArgs& p, cudaS
     return EVFLY_OK;
 }
 
+// rows of an `in`-row tensor that evfly_resize_bilinear_nhwc_bf16 (align_corners = False) reads when resizing to `out` rows. The
+// kernel computes its source row in fp32 (possibly contracted to an FMA); a row within 1e-3 of a boundary is marked on both sides.
+static void set_skip_rows(HaloArgs& p, int in, int out) {
+    p.use_rows = 0;
+    for (int i = 0; i < 16; ++i) p.row_mask[i] = 0u;
+    if (out <= 0 || in > 512 || in < 1) return;
+    auto mark = [&](int r) { if (r >= 0 && r < in) p.row_mask[r >> 5] |= 1u << (r & 31); };
+    const double scale = (double)in / (double)out;
+    for (int d = 0; d < out; ++d) {
+        double src = scale * (d + 0.5) - 0.5;
+        if (src < 0) src = 0;
+        const int i0 = (int)src;
+        mark(i0 < in - 1 ? i0 : in - 1);
+        mark(i0 + 1 < in - 1 ? i0 + 1 : in - 1);
+        if (src - i0 < 1e-3) mark(i0 - 1);
+        if (i0 + 1 - src < 1e-3) mark(i0 + 2 < in - 1 ? i0 + 2 : in - 1);
+    }
+    p.use_rows = 1;
+}
+
 static void set_tiles(HaloArgs& p) {
     p.tiles_x = (p.out_vw + 7) / 8;
     p.tiles_y = (p.out_vh + 15) / 16;
@@ -790,7 +816,7 @@ using namespace evfly;
 
 static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp, int Wp,
                      int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream, int pad = 0, const float* d_w1 = nullptr,
-                     const float* d_b1 = nullptr, float* d_out1 = nullptr) {
+                     const float* d_b1 = nullptr, float* d_out1 = nullptr, int skip_OH = 0) {
     EVFLY_REQUIRE(d_x && d_w && (d_out || d_out1) && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
     EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128) || (Cin == 128 && (Cout == 64 || Cout == 128 || Cout == 256)),
                   "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64}, (64,128) or (128, 64|128|256) (got %d, %d)", Cin, Cout);
@@ -811,6 +837,7 @@ static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void
     p.w1 = d_w1;
     p.b1 = d_b1;
     p.out1 = d_out1;
+    set_skip_rows(p, p.out_vh, skip_OH);
     EVFLY_REQUIRE((d_w1 == nullptr) == (d_out1 == nullptr) && (d_w1 == nullptr) == (d_b1 == nullptr), "tc_conv3x3_halo_out1_bf16: w1 / b1 / out1 go together");
     EVFLY_REQUIRE(d_out || !d_pool, "tc_conv3x3_halo_bf16: the fused pool needs the conv output");
     EVFLY_REQUIRE(!d_pool || (Hp2 >= (vh - 2) / 2 && Wp2 >= (vw - 2) / 2), "tc_conv3x3_halo_pool_bf16: pooled grid smaller than (vh-2)/2 x (vw-2)/2");
@@ -835,6 +862,12 @@ extern "C" int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w,
                                                int Wp, int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream) {
     EVFLY_REQUIRE(d_pool, "tc_conv3x3_halo_pool_bf16: null pool output");
     return halo_conv(d_x, d_w, d_bias, d_out, d_pool, N, Hp, Wp, vh, vw, Cin, Cout, relu, Hp2, Wp2, stream);
+}
+
+extern "C" int evfly_tc_conv3x3_halo_pool_rows_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp,
+                                                    int Wp, int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, int skip_OH, void* stream) {
+    EVFLY_REQUIRE(d_pool && skip_OH >= 1, "tc_conv3x3_halo_pool_rows_bf16: needs the pool output and skip_OH >= 1");
+    return halo_conv(d_x, d_w, d_bias, d_out, d_pool, N, Hp, Wp, vh, vw, Cin, Cout, relu, Hp2, Wp2, stream, 0, nullptr, nullptr, nullptr, skip_OH);
 }
 
 extern "C" int evfly_tc_conv3x3_halo_out1_bf16(const void* d_x, const void* d_w, const float* d_bias, const float* d_w1, const float* d_b1, float* d_out1,
@@ -867,8 +900,22 @@ extern "C" int evfly_form_patterns(float* d_frames, float cutoff, uint16_t* d_pa
     return EVFLY_OK;
 }
 
+static int stem_e12(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w, const float* d_bias, void* d_out, void* d_pool,
+                    int N, int H, int W, int relu, int Hp2, int Wp2, int skip_OH, void* stream);
+
 extern "C" int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w, const float* d_bias,
                                            void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2, int Wp2, void* stream) {
+    return stem_e12(d_pat, d_stem_w, d_stem_b, d_w, d_bias, d_out, d_pool, N, H, W, relu, Hp2, Wp2, 0, stream);
+}
+
+extern "C" int evfly_tc_stem_e12_pool_rows_bf16(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w, const float* d_bias,
+                                                void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2, int Wp2, int skip_OH, void* stream) {
+    EVFLY_REQUIRE(skip_OH >= 1, "tc_stem_e12_pool_rows_bf16: skip_OH >= 1");
+    return stem_e12(d_pat, d_stem_w, d_stem_b, d_w, d_bias, d_out, d_pool, N, H, W, relu, Hp2, Wp2, skip_OH, stream);
+}
+
+static int stem_e12(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w, const float* d_bias, void* d_out, void* d_pool,
+                    int N, int H, int W, int relu, int Hp2, int Wp2, int skip_OH, void* stream) {
     EVFLY_REQUIRE(d_pat && d_stem_w && d_stem_b && d_w && d_out && N > 0 && H >= 5 && W >= 5, "tc_stem_e12_pool_bf16: bad argument");
     HaloArgs p;
     p.bias = d_bias;
@@ -889,6 +936,7 @@ extern "C" int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d
     p.w1 = nullptr;
     p.b1 = nullptr;
     p.out1 = nullptr;
+    set_skip_rows(p, p.out_vh, skip_OH);
     StemE12Args sa;
     sa.pat = d_pat;
     sa.stem_w = d_stem_w;

@@ -426,15 +426,28 @@ class OrigUNet(PackedModule):
         N, dev = im.shape[0], im.device
         b = lambda name: getattr(self, "unet_" + name).bias
         cv = lambda g, name: tc.conv3x3(g, W[name], b(name), relu=True)
-        cvp = lambda g, name: tc.conv3x3_pool(g, W[name], b(name), relu=True)     # conv + MaxPool2d(2), fused where it can be
+        # 'interp' skip: y_e1..y_e3 are only sampled by the decoder's bilinear resize to the heights below (the decoder level that
+        # takes y_e{k} works at twice the valid height of its input, which shrinks by 4 per level), so the fused-pool convs write
+        # only the rows it reads
+        skip_oh = {}
+        if self.skip_type == 'interp' and (not self.is_deployment or self.velpred in (1, 11)):
+            h = im.shape[2]
+            for _ in range(4):
+                h = (h - 4) // 2
+            vh = h - 4                                   # valid height of y_e5
+            for k in (4, 3, 2, 1):
+                skip_oh[k] = 2 * vh
+                vh = 2 * vh - 4
+        cvp = lambda g, name, k=None: tc.conv3x3_pool(g, W[name], b(name), relu=True, skip_rows=skip_oh.get(k))     # conv + MaxPool2d(2), fused where it can be
         if self.form_BEV == 2 and tc.FUSE_STEM and tc.USE_HALO and tc.FUSE_POOL and im.shape[1] == 1:
             # binary mask: unet_e11 is a 512-entry table lookup inside the e12 kernel, e11 never goes to HBM
             y_e1, p1 = tc.stem_e12_pool(im, self.unet_e11.weight, self.unet_e11.bias, W["e12"], b("e12"),
-                                        frames_cutoff=float(self.evs_min_cutoff) if getattr(self, "_fold_form_input", False) else None)
+                                        frames_cutoff=float(self.evs_min_cutoff) if getattr(self, "_fold_form_input", False) else None,
+                                        skip_rows=skip_oh.get(1))
         else:
-            y_e1, p1 = cvp(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12")
-        y_e2, p2 = cvp(cv(p1, "e21"), "e22")
-        y_e3, p3 = cvp(cv(p2, "e31"), "e32")
+            y_e1, p1 = cvp(tc.stem_conv3x3(im, self.unet_e11.weight, self.unet_e11.bias), "e12", 1)
+        y_e2, p2 = cvp(cv(p1, "e21"), "e22", 2)
+        y_e3, p3 = cvp(cv(p2, "e31"), "e32", 3)
         y_e4, p4 = cvp(cv(p3, "e41"), "e42")
         y_e5 = cv(cv(p4, "e51"), "e52")
 

@@ -17,6 +17,7 @@ BF16 = torch.bfloat16
 USE_HALO = True      # small-channel 3x3 convs through the halo-reuse kernel
 FUSE_POOL = True     # MaxPool2d(2) in the epilogue of the halo-reuse kernel
 PERSISTENT_SCAN = True   # ConvLSTM recurrence as one persistent launch with a grid barrier per step
+SKIP_ROWS = True         # fused-pool convs whose output only feeds the 'interp' skip write just the rows that resize samples
 FUSED_SCAN = True        # ... with the x half of the gate conv inside the step (no fp32 x-gate tensor); needs PERSISTENT_SCAN
 
 
@@ -76,16 +77,21 @@ def _call_halo(*args):
 
 
 def _call_halo_pool(*args):
-    _lib.check(_lib.load().evfly_tc_conv3x3_halo_pool_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_pool_bf16")
+    """15 arguments: evfly_tc_conv3x3_halo_pool_bf16; a 16th (skip_OH): the _rows variant."""
+    if len(args) == 16:
+        _lib.check(_lib.load().evfly_tc_conv3x3_halo_pool_rows_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_pool_rows_bf16")
+    else:
+        _lib.check(_lib.load().evfly_tc_conv3x3_halo_pool_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_pool_bf16")
 
 
 def _halo_ok(cin, cout):
     return USE_HALO and ((cin in (32, 64) and cout in (32, 64)) or (cin == 64 and cout == 128) or (cin == 128 and cout in (64, 128, 256)))
 
 
-def conv3x3_pool(g: Grid, w_packed, bias, relu=True):
+def conv3x3_pool(g: Grid, w_packed, bias, relu=True, skip_rows=None):
     """conv3x3 followed by MaxPool2d(2): returns (conv output, pooled output). The pool is fused into the conv
-    epilogue on the halo path, a separate pass otherwise; the two are bit-identical."""
+    epilogue on the halo path, a separate pass otherwise; the two are bit-identical. skip_rows = OH (halo path only): the conv
+    output will only be read by resize_bilinear_into(..., OH, ...); rows that resize does not sample are not written."""
     Cout = w_packed.shape[0]
     if not (_halo_ok(g.C, Cout) and FUSE_POOL):
         y = conv3x3(g, w_packed, bias, relu=relu)
@@ -93,8 +99,9 @@ def conv3x3_pool(g: Grid, w_packed, bias, relu=True):
     out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
     ph, pw = (g.vh - 2) // 2, (g.vw - 2) // 2
     pooled = new_grid(g.N, ph, pw, Cout, ph, pw, g.data.device)
-    _call_halo_pool(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), pooled.data.data_ptr(), g.N, g.Hp, g.Wp,
-                    g.vh, g.vw, g.C, Cout, int(relu), pooled.Hp, pooled.Wp)
+    args = (g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), pooled.data.data_ptr(), g.N, g.Hp, g.Wp,
+            g.vh, g.vw, g.C, Cout, int(relu), pooled.Hp, pooled.Wp)
+    _call_halo_pool(*args, int(skip_rows)) if (skip_rows and SKIP_ROWS) else _call_halo_pool(*args)
     return out, pooled
 
 
@@ -419,13 +426,19 @@ FUSE_STEM = True     # binary-input stem as a table lookup inside the e12 kernel
 
 
 def _call_stem_e12(*args):
-    _lib.check(_lib.load().evfly_tc_stem_e12_pool_bf16(*args, _lib.stream_ptr()), "evfly_tc_stem_e12_pool_bf16")
+    """13 arguments: evfly_tc_stem_e12_pool_bf16; a 14th (skip_OH): the _rows variant that only writes the y_e1 rows the skip reads."""
+    if len(args) == 14:
+        _lib.check(_lib.load().evfly_tc_stem_e12_pool_rows_bf16(*args, _lib.stream_ptr()), "evfly_tc_stem_e12_pool_rows_bf16")
+    else:
+        _lib.check(_lib.load().evfly_tc_stem_e12_pool_bf16(*args, _lib.stream_ptr()), "evfly_tc_stem_e12_pool_bf16")
 
 
-def stem_e12_pool(mask_f32, stem_w, stem_b, w_packed, bias, relu=True, frames_cutoff=None):
+def stem_e12_pool(mask_f32, stem_w, stem_b, w_packed, bias, relu=True, frames_cutoff=None, skip_rows=None):
     """Binary mask [N,1,H,W] -> (y_e1 grid, pooled grid): unet_e11 + unet_e12 + MaxPool2d(2) without e11 in HBM.
     frames_cutoff = c: the first argument is the NORMALISED FRAME instead; form_input's cutoff (in place, like the reference)
-    and the mask are folded into the pattern extraction (one pass, no mask tensor)."""
+    and the mask are folded into the pattern extraction (one pass, no mask tensor).
+    skip_rows = OH: y_e1 will only be read by resize_bilinear_into(..., OH, ...) (the 'interp' skip): the rows that resize does
+    not sample are not written (undefined content)."""
     N, _, H, W = mask_f32.shape
     dev = mask_f32.device
     pat = torch.empty((N, H - 2, W - 2), dtype=torch.int16, device=dev)
@@ -436,8 +449,9 @@ def stem_e12_pool(mask_f32, stem_w, stem_b, w_packed, bias, relu=True, frames_cu
     out = new_grid(N, H, W, 32, H - 4, W - 4, dev)
     ph, pw = (H - 4) // 2, (W - 4) // 2
     pooled = new_grid(N, ph, pw, 32, ph, pw, dev)
-    _call_stem_e12(pat.data_ptr(), _lib.ptr(stem_w.contiguous()), _lib.ptr(stem_b), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(),
-                   pooled.data.data_ptr(), N, H, W, int(relu), pooled.Hp, pooled.Wp)
+    args = (pat.data_ptr(), _lib.ptr(stem_w.contiguous()), _lib.ptr(stem_b), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(),
+            pooled.data.data_ptr(), N, H, W, int(relu), pooled.Hp, pooled.Wp)
+    _call_stem_e12(*args, int(skip_rows)) if (skip_rows and SKIP_ROWS) else _call_stem_e12(*args)
     return out, pooled
 
 

@@ -600,6 +600,16 @@ int evfly_form_patterns(float* d_frames, float cutoff, uint16_t* d_pat, int N, i
 int evfly_tc_stem_e12_pool_bf16(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w,
                                 const float* d_bias, void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2,
                                 int Wp2, void* stream);
+/* The two fused-pool convs when d_out (y_e1 / y_e2 / y_e3) is only going to be sampled by evfly_resize_bilinear_nhwc_bf16 to a
+ * height of skip_OH -- the decoder's 'interp' skip (learner_models.py:512-519), its only other consumer being the pooled
+ * output written here: output rows that resize does not read are NOT written (their content in d_out is undefined). With the
+ * deployed sizes that is 44-52 % of the full-resolution stores. d_pool and the written rows are those of the plain calls. */
+int evfly_tc_stem_e12_pool_rows_bf16(const uint16_t* d_pat, const float* d_stem_w, const float* d_stem_b, const void* d_w,
+                                     const float* d_bias, void* d_out, void* d_pool, int N, int H, int W, int relu, int Hp2,
+                                     int Wp2, int skip_OH, void* stream);
+int evfly_tc_conv3x3_halo_pool_rows_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool,
+                                         int N, int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, int Hp2,
+                                         int Wp2, int skip_OH, void* stream);
 
 /* ======================================================================================
  * STAGE-LEVEL entry points (evfly_b200/csrc/stages.cu): whole stages of the path enqueued from C++ on the caller's

@@ -270,6 +270,41 @@ def test_halo_conv_fused_maxpool_is_bit_identical_to_separate_pool(cuda_lib, N, 
     check_bf16(tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw), ref, "fused pool")
 
 
+@pytest.mark.parametrize("N,vh,vw,Cin,Cout,OH,OW", [(2, 130, 173, 64, 64, 34, 74), (1, 62, 83, 128, 128, 14, 34), (2, 40, 50, 32, 32, 7, 9),
+                                                    (1, 37, 29, 64, 64, 35, 27), (1, 40, 33, 32, 64, 76, 60), (3, 21, 17, 64, 64, 1, 1)])
+def test_pool_conv_writing_only_the_rows_the_skip_reads(cuda_lib, N, vh, vw, Cin, Cout, OH, OW):
+    """learner_models.py:512-519: with the 'interp' skip y_e{k} is read only by F.interpolate(..., bilinear) to the decoder's size.
+    The _rows variant of the fused-pool conv must leave that resize (and the pooled tensor) bit-identical while skipping the
+    rows it does not sample; down- and up-sampling ratios, OH = 1 and ratios that land on row boundaries are covered."""
+    x = bf(rnd(N, Cin, vh, vw, seed=4))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=5, scale=(9 * Cin) ** -0.5))
+    b = rnd(Cout, seed=6)
+    g = tc.nchw_to_grid(x.cuda(), vh, vw)
+    wp = tc.pack_conv3x3_weight(w.cuda())
+    y, pooled = tc.conv3x3_pool(g, wp, b.cuda(), relu=True)
+    cat_full = torch.zeros((N, OH, OW, 2 * Cout), dtype=BF, device="cuda")
+    tc.resize_bilinear_into(y, OH, OW, cat_full, 0)
+    # poison the output buffer the sparse variant writes into, so that a row it wrongly skips shows
+    import evfly_b200.tc as T_
+    orig_new = T_.new_grid
+    def poisoned(*a, **k):
+        gg = orig_new(*a, **k)
+        gg.data.fill_(float("nan"))
+        return gg
+    T_.new_grid = poisoned
+    try:
+        y2, pooled2 = tc.conv3x3_pool(g, wp, b.cuda(), relu=True, skip_rows=OH)
+    finally:
+        T_.new_grid = orig_new
+    cat_rows = torch.zeros_like(cat_full)
+    tc.resize_bilinear_into(y2, OH, OW, cat_rows, 0)
+    assert torch.equal(cat_rows, cat_full)
+    assert torch.equal(tc.grid_to_nchw(pooled2.data, pooled2.vh, pooled2.vw), tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw))
+    written = ~torch.isnan(y2.data[:, :y2.vh, :y2.vw].float()).all(dim=(0, 2, 3))
+    if OH * 3 < y2.vh:
+        assert written.sum().item() <= 2 * OH + 2 and written.sum().item() < y2.vh        # it really skipped rows
+
+
 @pytest.mark.parametrize("T,P,Cx,Ch", [(12, 204, 512, 512), (6, 3264, 512, 512), (9, 816, 256, 512), (3, 100, 64, 64), (5, 5000, 512, 512)])
 def test_fused_convlstm_scan(cuda_lib, T, P, Cx, Ch):
     """convlstm.py:44-53 with the x half of the gate conv inside the persistent step kernel (csrc/convlstm_scan.cu): against the
