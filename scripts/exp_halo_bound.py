@@ -1,4 +1,6 @@
-"""Elimination experiment (temporary debug switches in tc_conv_halo.cu): which role bounds k_tc_stem_e12 and the halo convs."""
+"""Elimination experiment (temporary debug switches in tc_conv_halo.cu): which role bounds k_tc_stem_e12 and the halo convs.
+NOTE: the EVFLY_STEM_DBG / EVFLY_HALO_DBG switches this script drives were temporary instrumentation in tc_conv_halo.cu (roles reduced to
+their barrier traffic, wait flavours); they are not in the shipped kernels. Results: profiles/r2_exp_halo_roles.txt."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,6 @@
-"""Timeline of CTA 0 of k_tc_stem_e12 (temporary instrumentation): clock64 at the role hand-offs of its first 64 tiles."""
+"""Timeline of CTA 0 of k_tc_stem_e12 (temporary instrumentation): clock64 at the role hand-offs of its first 64 tiles.
+NOTE: needs the temporary clock64 instrumentation of k_tc_stem_e12 (EVFLY_STEM_TL), which is not in the shipped kernel.
+Results: profiles/r2_exp_halo_roles.txt (timeline paragraph)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
