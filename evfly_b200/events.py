@@ -76,8 +76,8 @@ CHUNK_EVENTS = 8192        # evfly_accumulate_chunk_events(): the device sorts w
 def pack_ev4_host(records: np.ndarray, edges_ns: np.ndarray):
     """Host-side packer of the 4-byte wire format: EVENT_DTYPE records of ONE time-sorted stream + window edges int64 [T+1] ->
     (uint32 records [m], win_offsets int64 [T+1], chunk_base_us uint32 [sum_w ceil(n_w / CHUNK_EVENTS)]) or None when the stream
-    cannot be represented exactly (times or edges off the 1 us grid, not sorted). Events that can never count (outside the
-    windows, polarity >= 2) are dropped here; chunk_base_us[c] is the offset from the window's first edge of the last record
+    cannot be represented exactly (times or edges off the 1 us grid, not sorted, coordinates >= (1023, 511)). Events that can
+    never count (outside the windows, polarity >= 2) are dropped here; chunk_base_us[c] is the offset from the window's first edge of the last record
     before chunk c of that window."""
     t = records_time_ns(records)
     edges_ns = np.asarray(edges_ns, dtype=np.int64)
@@ -88,8 +88,10 @@ def pack_ev4_host(records: np.ndarray, edges_ns: np.ndarray):
     lo, hi = int(offsets[0]), int(offsets[-1])
     r, tt = records[lo:hi], t[lo:hi]
     w = np.clip(np.searchsorted(offsets, np.arange(lo, hi), side="right") - 1, 0, T - 1)
-    keep = (r["polarity"] < 2) & (r["x"] < 1023) & (r["y"] < 511)
+    keep = r["polarity"] < 2
     r, tt, w = r[keep], tt[keep], w[keep]
+    if r.size and (int(r["x"].max()) >= 1023 or int(r["y"].max()) >= 511):
+        return None                      # coordinates beyond the record's 10 + 9 bits (a larger sensor): the 8-byte record takes them
     dt = tt - edges_ns[w]
     if (dt % 1000).any():
         return None

@@ -46,3 +46,6 @@ def test_pack_ev4_refuses_what_it_cannot_represent():
     assert pack_ev4_host(rec[::-1].copy(), edges) is None                      # not sorted by time
     assert pack_ev4_host(rec, edges + 1) is None                               # edges off the grid
     assert pack_ev4_host(rec, edges) is not None
+    big = rec.copy()
+    big["x"][5] = 1100                                                        # a sensor wider than 1023 pixels
+    assert pack_ev4_host(big, edges) is None
