@@ -95,7 +95,7 @@ class TcConvArgs(C.Structure):
                 ("M_rows", _i64), ("out_ld", _i64),
                 ("Cin", _i32), ("n_rows", _i32), ("taps", _i32), ("w_pitch", _i32), ("relu", _i32), ("out_c0", _i32),
                 ("convt", _i32), ("Hp", _i32), ("Wp", _i32), ("valid_h", _i32), ("valid_w", _i32), ("cout_t", _i32),
-                ("res_bf16", _vp), ("reserved", _i64), ("lstm_c", _vp), ("lstm_h", _vp)]
+                ("res_bf16", _vp), ("flags", _i64), ("lstm_c", _vp), ("lstm_h", _vp)]
 
 
 SIGNATURES.update({
@@ -190,6 +190,7 @@ def load() -> C.CDLL:
     return lib
 
 
+TC_COMPACT = 1            # EVFLY_TC_COMPACT
 ERR_UNSUPPORTED = -4      # EVFLY_ERR_UNSUPPORTED (include/evfly_b200.h)
 
 

@@ -86,10 +86,14 @@ static inline bool halo_ok(int cin, int cout) {
     return ((cin == 32 || cin == 64) && (cout == 32 || cout == 64)) || (cin == 64 && cout == 128) || (cin == 128 && (cout == 64 || cout == 128 || cout == 256));
 }
 
-// 3x3 valid conv + bias + ReLU on the pitch grid (+ optional MaxPool2d(2) of the result), the dispatch of tc.conv3x3(_pool)
+// 3x3 valid conv + bias + ReLU on the pitch grid (+ optional MaxPool2d(2) of the result), the dispatch of tc.conv3x3(_pool).
+// *oHp x *oWp: pitch of `out` -- the input's on the halo kernels, the output's own valid extent on the generic kernel
+// (EVFLY_TC_COMPACT: the next conv / the ConvLSTM then computes no don't-care rows).
 static int conv3(const void* x, int N, int Hp, int Wp, int vh, int vw, int Cin, const void* w, const float* b, int Cout, void* out, void* pool,
-                 int Hp2, int Wp2, void* st, int skip_OH = 0) {
+                 int Hp2, int Wp2, void* st, int* oHp, int* oWp, int skip_OH = 0) {
     if (halo_ok(Cin, Cout)) {
+        *oHp = Hp;
+        *oWp = Wp;
         if (pool && skip_OH > 0) return evfly_tc_conv3x3_halo_pool_rows_bf16(x, w, b, out, pool, N, Hp, Wp, vh, vw, Cin, Cout, 1, Hp2, Wp2, skip_OH, st);
         if (pool) return evfly_tc_conv3x3_halo_pool_bf16(x, w, b, out, pool, N, Hp, Wp, vh, vw, Cin, Cout, 1, Hp2, Wp2, st);
         return evfly_tc_conv3x3_halo_bf16(x, w, b, out, N, Hp, Wp, vh, vw, Cin, Cout, 1, st);
@@ -107,8 +111,13 @@ static int conv3(const void* x, int N, int Hp, int Wp, int vh, int vw, int Cin, 
     a.taps = 9;
     a.w_pitch = Wp;
     a.relu = 1;
+    a.flags = EVFLY_TC_COMPACT;
+    a.Hp = Hp;
+    a.Wp = Wp;
+    a.valid_h = *oHp = vh - 2;
+    a.valid_w = *oWp = vw - 2;
     int rc = evfly_tc_conv_bf16(&a, st);
-    if (!rc && pool) rc = evfly_maxpool2x2_nhwc_bf16(out, pool, N, Hp, Wp, vh - 2, vw - 2, Cout, st);
+    if (!rc && pool) rc = evfly_maxpool2x2_nhwc_bf16(out, pool, N, vh - 2, vw - 2, vh - 2, vw - 2, Cout, st);
     return rc;
 }
 
@@ -222,6 +231,7 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
     // ---- form_input (learner_models.py:476-494, form_BEV = 2: cutoff in place on the caller's frames, 0/1 mask) fused with the
     //      extraction of the stem's 3x3 mask patterns; ---- encoder (learner_models.py:533-541)
     void* ye[5];
+    int yeHp[5] = {H, 0, 0, 0, 0}, yeWp[5] = {W, 0, 0, 0, 0};      // pitch of y_e{l+1}
     {
         uint16_t* pat = (uint16_t*)ws.take((int64_t)N * (H - 2) * (W - 2) * 2);
         RC(evfly_form_patterns(d_frames, cutoff, pat, N, H, W, stream));
@@ -244,14 +254,15 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
             void* c1 = ws.take(px * C * 2);
             ye[l] = ws.take(px * C * 2);
             void* nxt = l < 4 ? ws.take((int64_t)N * g.Hp[l + 1] * g.Wp[l + 1] * C * 2) : nullptr;
-            RC(conv3(x, N, Hp, Wp, Hp, Wp, Cin, wts->conv_w[2 * l - 1], wts->conv_b[2 * l - 1], C, c1, nullptr, 0, 0, stream));
-            RC(conv3(c1, N, Hp, Wp, Hp - 2, Wp - 2, C, wts->conv_w[2 * l], wts->conv_b[2 * l], C, ye[l], nxt, l < 4 ? g.Hp[l + 1] : 0, l < 4 ? g.Wp[l + 1] : 0, stream,
-                     l < 3 ? skip_oh[l] : 0));
+            int h1, w1;
+            RC(conv3(x, N, Hp, Wp, Hp, Wp, Cin, wts->conv_w[2 * l - 1], wts->conv_b[2 * l - 1], C, c1, nullptr, 0, 0, stream, &h1, &w1));
+            RC(conv3(c1, N, h1, w1, Hp - 2, Wp - 2, C, wts->conv_w[2 * l], wts->conv_b[2 * l], C, ye[l], nxt, l < 4 ? g.Hp[l + 1] : 0, l < 4 ? g.Wp[l + 1] : 0, stream,
+                     &yeHp[l], &yeWp[l], l < 3 ? skip_oh[l] : 0));
             x = nxt;
         }
     }
     // ---- ConvLSTM over time (learner_models.py:544-546; convlstm.py:136-176), n_traj trajectories side by side
-    const int Hp5 = g.Hp[4], Wp5 = g.Wp[4], vh5 = g.ev[4][0], vw5 = g.ev[4][1], Ch = 512;
+    const int Hp5 = yeHp[4], Wp5 = yeWp[4], vh5 = g.ev[4][0], vw5 = g.ev[4][1], Ch = 512;
     const int64_t P = (int64_t)n_traj * Hp5 * Wp5;
     float* gx = (float*)ws.take((int64_t)T * P * 4 * Ch * 4);
     __nv_bfloat16* h_all = (__nv_bfloat16*)ws.take((int64_t)(T + 1) * P * Ch * 2);
@@ -293,19 +304,22 @@ extern "C" int evfly_unet_forward(const evfly_unet_weights* wts, float* d_frames
         void* d2 = ws.take(px * C * 2);
         EVFLY_REQUIRE(ws.ok, "unet_forward: workspace exhausted (internal sizing error)");
         const int el = 4 - lvl;           // encoder level whose output is skipped in
-        RC(evfly_resize_bilinear_nhwc_bf16(ye[el], cat, N, g.Hp[el], g.Wp[el], g.ev[el][0], g.ev[el][1], C, oh, ow, 2 * C, 0, stream));
+        RC(evfly_resize_bilinear_nhwc_bf16(ye[el], cat, N, yeHp[el], yeWp[el], g.ev[el][0], g.ev[el][1], C, oh, ow, 2 * C, 0, stream));
         RC(convt2x2(y, N, yHp, yWp, yvh, yvw, Cin, wts->up_w[lvl - 1], wts->up_b[lvl - 1], C, cat, 2 * C, C, stream));
-        RC(conv3(cat, N, oh, ow, oh, ow, 2 * C, wts->conv_w[9 + 2 * (lvl - 1)], wts->conv_b[9 + 2 * (lvl - 1)], C, d1, nullptr, 0, 0, stream));
+        int h1, w1, h2 = oh, w2 = ow;
+        RC(conv3(cat, N, oh, ow, oh, ow, 2 * C, wts->conv_w[9 + 2 * (lvl - 1)], wts->conv_b[9 + 2 * (lvl - 1)], C, d1, nullptr, 0, 0, stream, &h1, &w1));
         if (lvl == 4) {
             // unet_d42 with unet_out (1x1 to one channel, :583) in its epilogue: the 32-channel activation is never written
             out32 = (float*)d2;       // N*oh*ow fp32 fit the N*oh*ow*32 bf16 reserved for d42's output
-            RC(evfly_tc_conv3x3_halo_out1_bf16(d1, wts->conv_w[16], wts->conv_b[16], wts->out_w, wts->out_b, out32, N, oh, ow, oh - 2, ow - 2, C, C, 1, stream));
+            RC(evfly_tc_conv3x3_halo_out1_bf16(d1, wts->conv_w[16], wts->conv_b[16], wts->out_w, wts->out_b, out32, N, h1, w1, oh - 2, ow - 2, C, C, 1, stream));
+            h2 = h1;
+            w2 = w1;
         } else {
-            RC(conv3(d1, N, oh, ow, oh - 2, ow - 2, C, wts->conv_w[10 + 2 * (lvl - 1)], wts->conv_b[10 + 2 * (lvl - 1)], C, d2, nullptr, 0, 0, stream));
+            RC(conv3(d1, N, h1, w1, oh - 2, ow - 2, C, wts->conv_w[10 + 2 * (lvl - 1)], wts->conv_b[10 + 2 * (lvl - 1)], C, d2, nullptr, 0, 0, stream, &h2, &w2));
         }
         y = d2;
-        yHp = oh;
-        yWp = ow;
+        yHp = h2;
+        yWp = w2;
         yvh = oh - 4;
         yvw = ow - 4;
     }

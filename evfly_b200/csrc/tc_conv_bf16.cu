@@ -49,6 +49,9 @@ struct TcArgs {
     int bias_mod;
     // transposed-conv scatter: GEMM column n = phase*cout_t + co, phase = 2a+b
     int convt, Hp, Wp, valid_h, valid_w, cout_t;
+    // compact output: row m = (img, ih, iw) of the source grid [N,Hp,Wp] goes to pixel (img*valid_h + ih)*valid_w + iw of a
+    // [N, valid_h, valid_w] grid, rows outside valid_h x valid_w are skipped (the next conv then has no don't-care rows to compute)
+    int compact;
 };
 
 template <int TN, int KC>
@@ -270,13 +273,14 @@ k_tc_conv_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             long long dst_pix = m;
             int ih = 0, iw = 0;
             long long img = 0;
-            if (p.convt) {
+            if (p.convt || p.compact) {
                 const long long hw = (long long)p.Hp * p.Wp;
                 img = m / hw;
                 const int rem = (int)(m - img * hw);
                 ih = rem / p.Wp;
                 iw = rem - ih * p.Wp;
                 row_ok = row_ok && ih < p.valid_h && iw < p.valid_w;
+                if (p.compact) dst_pix = (img * p.valid_h + ih) * (long long)p.valid_w + iw;
             }
 #pragma unroll 1
             for (int c0 = 0; c0 < TN; c0 += 32) {
@@ -561,6 +565,9 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     EVFLY_REQUIRE(a.Cin % 32 == 0, "tc_conv_bf16: Cin must be a multiple of 32 (got %d)", a.Cin);
     EVFLY_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0, "tc_conv_bf16: operands must be 16-byte aligned");
     EVFLY_REQUIRE(!(a.convt && (a.res_f32 || a.res_bf16)), "tc_conv_bf16: residuals are not supported with convt");
+    EVFLY_REQUIRE(!(a.flags & EVFLY_TC_COMPACT) || (!a.convt && !a.lstm_c && !a.res_f32 && !a.res_bf16 && a.Hp > 0 && a.Wp > 0 && a.valid_h >= 1 && a.valid_h <= a.Hp &&
+                                                    a.valid_w >= 1 && a.valid_w <= a.Wp && a.M_rows % ((int64_t)a.Hp * a.Wp) == 0),
+                  "tc_conv_bf16: EVFLY_TC_COMPACT needs Hp, Wp, valid_h <= Hp, valid_w <= Wp, M_rows = N*Hp*Wp and no residual / convt / lstm");
     EVFLY_REQUIRE(!a.convt || (a.taps == 1 && a.cout_t % 32 == 0 && a.n_rows == 4 * a.cout_t && a.Hp > 0 && a.Wp > 0 && a.valid_h <= a.Hp && a.valid_w <= a.Wp),
                   "tc_conv_bf16: bad transposed-conv arguments");
     TcArgs p;
@@ -590,6 +597,7 @@ extern "C" int evfly_tc_conv_bf16(const evfly_tc_conv_args* args, void* stream) 
     p.valid_h = a.valid_h;
     p.valid_w = a.valid_w;
     p.cout_t = a.cout_t;
+    p.compact = (int)(a.flags & EVFLY_TC_COMPACT);
     cudaStream_t st = (cudaStream_t)stream;
     const bool kc64 = (a.Cin % 64 == 0);
     // N tile: the whole weight matrix when it fits 256 accumulator columns, else 256-wide tiles;

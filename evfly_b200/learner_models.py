@@ -425,7 +425,7 @@ class OrigUNet(PackedModule):
     def _unet_bf16(self, im, state, W, n_traj=1):
         N, dev = im.shape[0], im.device
         b = lambda name: getattr(self, "unet_" + name).bias
-        cv = lambda g, name: tc.conv3x3(g, W[name], b(name), relu=True)
+        cv = lambda g, name: tc.conv3x3(g, W[name], b(name), relu=True, compact=True)      # wide layers write compact grids (no don't-care rows downstream)
         # 'interp' skip: y_e1..y_e3 are only sampled by the decoder's bilinear resize to the heights below (the decoder level that
         # takes y_e{k} works at twice the valid height of its input, which shrinks by 4 per level), so the fused-pool convs write
         # only the rows it reads

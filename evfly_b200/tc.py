@@ -17,6 +17,7 @@ BF16 = torch.bfloat16
 USE_HALO = True      # small-channel 3x3 convs through the halo-reuse kernel
 FUSE_POOL = True     # MaxPool2d(2) in the epilogue of the halo-reuse kernel
 PERSISTENT_SCAN = True   # ConvLSTM recurrence as one persistent launch with a grid barrier per step
+COMPACT_GRIDS = True     # wide (generic-kernel) 3x3 convs write compact grids: no don't-care rows in the next conv / the ConvLSTM
 SKIP_ROWS = True         # fused-pool convs whose output only feeds the 'interp' skip write just the rows that resize samples
 FUSED_SCAN = True        # ... with the x half of the gate conv inside the step (no fp32 x-gate tensor); needs PERSISTENT_SCAN
 
@@ -94,7 +95,7 @@ def conv3x3_pool(g: Grid, w_packed, bias, relu=True, skip_rows=None):
     output will only be read by resize_bilinear_into(..., OH, ...); rows that resize does not sample are not written."""
     Cout = w_packed.shape[0]
     if not (_halo_ok(g.C, Cout) and FUSE_POOL):
-        y = conv3x3(g, w_packed, bias, relu=relu)
+        y = conv3x3(g, w_packed, bias, relu=relu, compact=True)
         return y, maxpool2x2(y)
     out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
     ph, pw = (g.vh - 2) // 2, (g.vw - 2) // 2
@@ -130,11 +131,15 @@ def _call(a: _lib.TcConvArgs):
     _lib.check(_lib.load().evfly_tc_conv_bf16(C.byref(a), _lib.stream_ptr()), "evfly_tc_conv_bf16")
 
 
-def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None) -> Grid:
-    """3x3 valid conv (+bias, ReLU) on the grid; the result keeps the pitch, valid extent - 2."""
+def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None, compact=False) -> Grid:
+    """3x3 valid conv (+bias, ReLU) on the grid; the result keeps the pitch, valid extent - 2. compact=True (wide layers on
+    the generic kernel only; the halo kernels compute no don't-care tiles anyway): the result is written on a grid whose pitch
+    IS its valid extent, so the next layer has no don't-care rows to compute."""
     Cout = w_packed.shape[0]
+    compact = bool(compact) and COMPACT_GRIDS and out is None and not _halo_ok(g.C, Cout)
     if out is None:
-        out = new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device)
+        out = (new_grid(g.N, g.vh - 2, g.vw - 2, Cout, g.vh - 2, g.vw - 2, g.data.device) if compact else
+               new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device))
     if _halo_ok(g.C, Cout):
         # small-channel layers: halo reuse from shared memory, weights resident (tc_conv_halo.cu)
         _call_halo(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C, Cout, int(relu))
@@ -143,6 +148,8 @@ def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None) -> Grid
     a.x, a.w, a.bias, a.out = g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr()
     a.M_rows, a.out_ld = g.rows, Cout
     a.Cin, a.n_rows, a.taps, a.w_pitch, a.relu, a.out_c0 = g.C, Cout, 9, g.Wp, int(relu), 0
+    if compact:
+        a.flags, a.Hp, a.Wp, a.valid_h, a.valid_w = _lib.TC_COMPACT, g.Hp, g.Wp, g.vh - 2, g.vw - 2
     _call(a)
     return out
 

@@ -426,6 +426,11 @@ int evfly_velpred_unit_f32(const float* d_y, float* d_out, int N, void* stream);
  *              pixel (img, 2*ih+a, 2*iw+b) of the compact grid [N, 2*valid_h, 2*valid_w]; rows of
  *              the source grid [N,Hp,Wp] outside valid_h x valid_w are skipped.
  * Cin must be a multiple of 32.                                                              */
+/* flags: EVFLY_TC_COMPACT -- write the result on a COMPACT grid [N, valid_h, valid_w, ...] instead of the source's pitch grid:
+ * row (n, ih, iw) of [N,Hp,Wp] with ih < valid_h, iw < valid_w (give the OUTPUT's valid extent) goes to pixel
+ * (n*valid_h + ih)*valid_w + iw, other rows are skipped. The second 3x3 conv of a UNet level then runs on (Hp-2)(Wp-2) rows
+ * instead of Hp*Wp, the ConvLSTM on 8x13 instead of 12x17 positions per frame.                                              */
+#define EVFLY_TC_COMPACT 1
 typedef struct evfly_tc_conv_args {
     const void*  x;
     const void*  w;
@@ -438,7 +443,7 @@ typedef struct evfly_tc_conv_args {
     int32_t Cin, n_rows, taps, w_pitch, relu, out_c0;
     int32_t convt, Hp, Wp, valid_h, valid_w, cout_t;
     const void*  res_bf16;   /* optional bf16 [M_rows, n_rows] residual (x + attn(x), x + ffn(x)) */
-    int64_t reserved;        /* must be 0 */
+    int64_t flags;           /* 0, or EVFLY_TC_COMPACT */
     /* fused ConvLSTM cell (convlstm.py:44-53): with weight rows interleaved as n = 4*ch + gate
      * (gate order i,f,o,g) the epilogue computes c = sig(f)*c + sig(i)*tanh(g), h = sig(o)*tanh(c)
      * in place on lstm_c fp32 [M_rows, n_rows/4] and writes h as bf16 [M_rows, n_rows/4]; the gate

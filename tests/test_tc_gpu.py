@@ -270,6 +270,26 @@ def test_halo_conv_fused_maxpool_is_bit_identical_to_separate_pool(cuda_lib, N, 
     check_bf16(tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw), ref, "fused pool")
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(3, 12, 17, 256, 512), (2, 29, 39, 256, 256), (1, 16, 26, 512, 256), (5, 5, 7, 256, 256)])
+def test_generic_conv_compact_output(cuda_lib, N, H, W, Cin, Cout):
+    """EVFLY_TC_COMPACT: the wide layers write their result on a grid whose pitch is the valid extent; the valid pixels are those of
+    the pitch-preserving call bit for bit, and a second conv on the compact grid equals the second conv on the pitch grid."""
+    x = bf(rnd(N, Cin, H, W, seed=1))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5))
+    b = rnd(Cout, seed=3)
+    g = tc.nchw_to_grid(x.cuda(), H, W)
+    wp = tc.pack_conv3x3_weight(w.cuda())
+    y_pitch = tc.conv3x3(g, wp, b.cuda(), relu=True)
+    y_comp = tc.conv3x3(g, wp, b.cuda(), relu=True, compact=True)
+    assert (y_comp.Hp, y_comp.Wp, y_comp.vh, y_comp.vw) == (H - 2, W - 2, H - 2, W - 2) and (y_pitch.Hp, y_pitch.Wp) == (H, W)
+    assert torch.equal(y_comp.data, y_pitch.data[:, :H - 2, :W - 2].contiguous())
+    if H >= 7 and Cout % 32 == 0:
+        w2 = tc.pack_conv3x3_weight(bf(rnd(Cout, Cout, 3, 3, seed=5, scale=(9 * Cout) ** -0.5)).cuda())
+        z_pitch = tc.conv3x3(y_pitch, w2, None, relu=False)
+        z_comp = tc.conv3x3(y_comp, w2, None, relu=False, compact=True)
+        assert torch.equal(z_comp.data, z_pitch.data[:, :H - 4, :W - 4].contiguous())
+
+
 @pytest.mark.parametrize("N,vh,vw,Cin,Cout,OH,OW", [(2, 130, 173, 64, 64, 34, 74), (1, 62, 83, 128, 128, 14, 34), (2, 40, 50, 32, 32, 7, 9),
                                                     (1, 37, 29, 64, 64, 35, 27), (1, 40, 33, 32, 64, 76, 60), (3, 21, 17, 64, 64, 1, 1)])
 def test_pool_conv_writing_only_the_rows_the_skip_reads(cuda_lib, N, vh, vw, Cin, Cout, OH, OW):
