@@ -336,9 +336,9 @@ class TrajectoryEvalWorkload:
         orig = {h: getattr(tc, h) for h in hooks}
 
         def timed(fn):
-            def wrapper(*a):
+            def wrapper(*a, **k):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); r = fn(*a); e1.record()
+                e0.record(); r = fn(*a, **k); e1.record()
                 self._ev.append((e0, e1))
                 return r
             return wrapper

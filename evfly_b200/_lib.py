@@ -115,6 +115,7 @@ SIGNATURES.update({
     "evfly_attention_small_bf16": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "evfly_dwconv3x3_gelu_nhwc_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "evfly_tc_conv3x3_halo_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evfly_tc_conv3x3_halo_compact_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_tc_conv3x3_halo_out1_bf16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_tc_conv3x3_same_bf16": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evfly_shuffle_upsample_cat_bf16": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),

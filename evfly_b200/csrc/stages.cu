@@ -87,16 +87,16 @@ static inline bool halo_ok(int cin, int cout) {
 }
 
 // 3x3 valid conv + bias + ReLU on the pitch grid (+ optional MaxPool2d(2) of the result), the dispatch of tc.conv3x3(_pool).
-// *oHp x *oWp: pitch of `out` -- the input's on the halo kernels, the output's own valid extent on the generic kernel
-// (EVFLY_TC_COMPACT: the next conv / the ConvLSTM then computes no don't-care rows).
+// *oHp x *oWp: pitch of `out` -- its own valid extent (compact grids: a consumer that computes every row of its grid -- the generic
+// kernel, the transposed convs, the ConvLSTM -- then has no don't-care rows), the input's for the fused-pool convs (the skip reads those).
 static int conv3(const void* x, int N, int Hp, int Wp, int vh, int vw, int Cin, const void* w, const float* b, int Cout, void* out, void* pool,
                  int Hp2, int Wp2, void* st, int* oHp, int* oWp, int skip_OH = 0) {
     if (halo_ok(Cin, Cout)) {
-        *oHp = Hp;
-        *oWp = Wp;
+        *oHp = pool ? Hp : vh - 2;
+        *oWp = pool ? Wp : vw - 2;
         if (pool && skip_OH > 0) return evfly_tc_conv3x3_halo_pool_rows_bf16(x, w, b, out, pool, N, Hp, Wp, vh, vw, Cin, Cout, 1, Hp2, Wp2, skip_OH, st);
         if (pool) return evfly_tc_conv3x3_halo_pool_bf16(x, w, b, out, pool, N, Hp, Wp, vh, vw, Cin, Cout, 1, Hp2, Wp2, st);
-        return evfly_tc_conv3x3_halo_bf16(x, w, b, out, N, Hp, Wp, vh, vw, Cin, Cout, 1, st);
+        return evfly_tc_conv3x3_halo_compact_bf16(x, w, b, out, N, Hp, Wp, vh, vw, Cin, Cout, 1, st);
     }
     evfly_tc_conv_args a;
     memset(&a, 0, sizeof(a));

@@ -33,6 +33,7 @@ struct HaloArgs {
     int Hp2, Wp2;
     int pad;              // 1: padding=1 conv on a dense tensor (Hp x Wp all valid): the halo box starts at (-1,-1) and TMA zero-fills outside the image
     int N, Hp, Wp, out_vh, out_vw;
+    int oHp, oWp;         // pitch of `out` / `out1`: the input's (Hp, Wp), or out_vh x out_vw for a compact output grid
     int tiles_x, tiles_y;
     uint32_t magic_x;     // floor(2^32 / tiles_x) + 1 when tiles_x * tiles_y < 65536 (then umulhi(rem, magic_x) == rem / tiles_x), else 0
     int relu;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                     // this pixel's chunk (c0/8 + q) -> staging row `lane`, chunk position XOR-swizzled (conflict-free)
                     sts128(my_row + (((uint32_t)((c0 >> 3) + q) ^ my_swz) << 4), val);
                 } else {
-                    if (ok && row_wanted(p, oh)) reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + oh) * p.Wp + ow) * COUT + c0)[q] = val;
+                    if (ok && row_wanted(p, oh)) reinterpret_cast<uint4*>(p.out + (((long long)n * p.oHp + oh) * p.oWp + ow) * COUT + c0)[q] = val;
                     if (p.pool_out) {
                         // fused 2x2 max-pool: the partners of pixel (r, c) are lanes ^1 (column) and ^8 (row) of the same warp; the
                         // lane with even r and even c writes. max commutes with the (monotonic) bf16 rounding, so the result
@@ -192,7 +193,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                 }
             }
         }
-        if (p.w1 && ok) p.out1[((long long)n * p.Hp + oh) * p.Wp + ow] = dot1 + __ldg(p.b1);
+        if (p.w1 && ok) p.out1[((long long)n * p.oHp + oh) * p.oWp + ow] = dot1 + __ldg(p.b1);
         if constexpr (kStage) if (p.out) {
             __syncwarp();
             if (p.pool_out) {
@@ -221,7 +222,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloArgs& p, int warp, int l
                 const int poh = ty * 16 + ew * 4 + (px >> 3), pow_ = tx * 8 + (px & 7);
                 if (poh < p.out_vh && pow_ < p.out_vw && row_wanted(p, poh)) {
                     const uint4 val = lds128(my_stage + px * (COUT * 2) + ((ch ^ (kCP == 4 ? ((px >> 1) & 3) : (px & 7))) << 4));
-                    *reinterpret_cast<uint4*>(p.out + (((long long)n * p.Hp + poh) * p.Wp + pow_) * COUT + ch * 8) = val;
+                    *reinterpret_cast<uint4*>(p.out + (((long long)n * p.oHp + poh) * p.oWp + pow_) * COUT + ch * 8) = val;
                 }
             }
             __syncwarp();      // the staging rows are rewritten by the next tile of this warp
@@ -816,7 +817,7 @@ using namespace evfly;
 
 static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp, int Wp,
                      int vh, int vw, int Cin, int Cout, int relu, int Hp2, int Wp2, void* stream, int pad = 0, const float* d_w1 = nullptr,
-                     const float* d_b1 = nullptr, float* d_out1 = nullptr, int skip_OH = 0) {
+                     const float* d_b1 = nullptr, float* d_out1 = nullptr, int skip_OH = 0, int compact = 0) {
     EVFLY_REQUIRE(d_x && d_w && (d_out || d_out1) && N > 0 && Hp >= 3 && Wp >= 3 && vh >= 3 && vw >= 3 && vh <= Hp && vw <= Wp, "tc_conv3x3_halo_bf16: bad shape");
     EVFLY_REQUIRE(((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || (Cin == 64 && Cout == 128) || (Cin == 128 && (Cout == 64 || Cout == 128 || Cout == 256)),
                   "tc_conv3x3_halo_bf16: (Cin, Cout) must be in {32,64}x{32,64}, (64,128) or (128, 64|128|256) (got %d, %d)", Cin, Cout);
@@ -829,6 +830,8 @@ static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void
     p.pad = pad;
     p.out_vh = vh - 2 + 2 * pad;
     p.out_vw = vw - 2 + 2 * pad;
+    p.oHp = compact ? p.out_vh : Hp;
+    p.oWp = compact ? p.out_vw : Wp;
     set_tiles(p);
     p.relu = relu;
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(d_pool);
@@ -856,6 +859,11 @@ static int halo_conv(const void* d_x, const void* d_w, const float* d_bias, void
 extern "C" int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int Hp, int Wp,
                                           int vh, int vw, int Cin, int Cout, int relu, void* stream) {
     return halo_conv(d_x, d_w, d_bias, d_out, nullptr, N, Hp, Wp, vh, vw, Cin, Cout, relu, 0, 0, stream);
+}
+
+extern "C" int evfly_tc_conv3x3_halo_compact_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N, int Hp, int Wp,
+                                                  int vh, int vw, int Cin, int Cout, int relu, void* stream) {
+    return halo_conv(d_x, d_w, d_bias, d_out, nullptr, N, Hp, Wp, vh, vw, Cin, Cout, relu, 0, 0, stream, 0, nullptr, nullptr, nullptr, 0, 1);
 }
 
 extern "C" int evfly_tc_conv3x3_halo_pool_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, void* d_pool, int N, int Hp,
@@ -926,6 +934,8 @@ static int stem_e12(const uint16_t* d_pat, const float* d_stem_w, const float* d
     p.pad = 0;
     p.out_vh = H - 4;
     p.out_vw = W - 4;
+    p.oHp = H;
+    p.oWp = W;
     set_tiles(p);
     p.relu = relu;
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(d_pool);

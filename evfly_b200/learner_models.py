@@ -480,7 +480,7 @@ class OrigUNet(PackedModule):
                     # unet_d42 with unet_out (1x1 to one channel) in its epilogue: the 32-channel activation is never written
                     y1 = cv(tc.Grid(cat, oh, ow), "d41")
                     out32 = tc.conv3x3_out1(y1, W["d42"], b("d42"), W["out_w1"], self.unet_out.bias)
-                    y = tc.Grid(out32.view(N, oh, ow, 1), oh - 4, ow - 4)
+                    y = tc.Grid(out32.view(N, y1.Hp, y1.Wp, 1), oh - 4, ow - 4)
                 else:
                     y = cv(cv(tc.Grid(cat, oh, ow), f"d{lvl}1"), f"d{lvl}2")
             if self.num_out_channels != 1:

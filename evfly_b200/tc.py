@@ -73,8 +73,11 @@ def _call_scan_fused(*args) -> bool:
     return True
 
 
-def _call_halo(*args):
-    _lib.check(_lib.load().evfly_tc_conv3x3_halo_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_bf16")
+def _call_halo(*args, compact=False):
+    if compact:
+        _lib.check(_lib.load().evfly_tc_conv3x3_halo_compact_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_compact_bf16")
+    else:
+        _lib.check(_lib.load().evfly_tc_conv3x3_halo_bf16(*args, _lib.stream_ptr()), "evfly_tc_conv3x3_halo_bf16")
 
 
 def _call_halo_pool(*args):
@@ -132,17 +135,18 @@ def _call(a: _lib.TcConvArgs):
 
 
 def conv3x3(g: Grid, w_packed, bias, relu=True, out: Grid | None = None, compact=False) -> Grid:
-    """3x3 valid conv (+bias, ReLU) on the grid; the result keeps the pitch, valid extent - 2. compact=True (wide layers on
-    the generic kernel only; the halo kernels compute no don't-care tiles anyway): the result is written on a grid whose pitch
-    IS its valid extent, so the next layer has no don't-care rows to compute."""
+    """3x3 valid conv (+bias, ReLU) on the grid; the result keeps the pitch, valid extent - 2. compact=True: the result is
+    written on a grid whose pitch IS its valid extent, so a consumer that computes every row of the grid it is given (the
+    generic kernel, the transposed convs, the ConvLSTM) has no don't-care rows to compute."""
     Cout = w_packed.shape[0]
-    compact = bool(compact) and COMPACT_GRIDS and out is None and not _halo_ok(g.C, Cout)
+    compact = bool(compact) and COMPACT_GRIDS and out is None
     if out is None:
         out = (new_grid(g.N, g.vh - 2, g.vw - 2, Cout, g.vh - 2, g.vw - 2, g.data.device) if compact else
                new_grid(g.N, g.Hp, g.Wp, Cout, g.vh - 2, g.vw - 2, g.data.device))
     if _halo_ok(g.C, Cout):
         # small-channel layers: halo reuse from shared memory, weights resident (tc_conv_halo.cu)
-        _call_halo(g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C, Cout, int(relu))
+        args = (g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr(), g.N, g.Hp, g.Wp, g.vh, g.vw, g.C, Cout, int(relu))
+        _call_halo(*args, compact=True) if compact else _call_halo(*args)
         return out
     a = _lib.TcConvArgs()
     a.x, a.w, a.bias, a.out = g.data.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias), out.data.data_ptr()

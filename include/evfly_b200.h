@@ -546,6 +546,10 @@ int evfly_lstm_seq_smemw(const float* d_gx, const void* d_whh_pairs, const float
  * out bf16 [N,Hp,Wp,Cout]; only the valid (vh-2) x (vw-2) outputs are written.                         */
 int evfly_tc_conv3x3_halo_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N,
                                int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, void* stream);
+/* The same conv writing a COMPACT grid: d_out bf16 [N, vh-2, vw-2, Cout] (pitch = valid extent, cf. EVFLY_TC_COMPACT): for layers
+ * whose consumer is the generic kernel or a transposed conv, which compute every row of the grid they are given.            */
+int evfly_tc_conv3x3_halo_compact_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_out, int N,
+                                       int Hp, int Wp, int vh, int vw, int Cin, int Cout, int relu, void* stream);
 
 /* The same conv with nn.MaxPool2d(2) (learner_models.py OrigUNet pool1..pool4) fused into the epilogue: besides
  * d_out it writes d_pool bf16 [N,Hp2,Wp2,Cout], valid ((vh-2)/2) x ((vw-2)/2), bit-identical to

@@ -36,8 +36,8 @@ for fn in _lib.SIGNATURES:
             if fn == "evfly_tc_conv_bf16":       # per-shape breakdown of the GEMM family
                 st = a[0]._obj if hasattr(a[0], "_obj") else a[0].contents
                 shapes[(st.M_rows, st.Cin, st.n_rows, st.taps, st.convt, st.Hp, st.Wp)].append((e0, e1))
-            if fn in ("evfly_tc_conv3x3_halo_bf16", "evfly_tc_conv3x3_halo_pool_bf16", "evfly_tc_conv3x3_halo_pool_rows_bf16", "evfly_tc_conv3x3_halo_out1_bf16"):
-                off = {"evfly_tc_conv3x3_halo_bf16": 4, "evfly_tc_conv3x3_halo_pool_bf16": 5, "evfly_tc_conv3x3_halo_pool_rows_bf16": 5, "evfly_tc_conv3x3_halo_out1_bf16": 6}[fn]
+            if fn in ("evfly_tc_conv3x3_halo_bf16", "evfly_tc_conv3x3_halo_compact_bf16", "evfly_tc_conv3x3_halo_pool_bf16", "evfly_tc_conv3x3_halo_pool_rows_bf16", "evfly_tc_conv3x3_halo_out1_bf16"):
+                off = {"evfly_tc_conv3x3_halo_bf16": 4, "evfly_tc_conv3x3_halo_compact_bf16": 4, "evfly_tc_conv3x3_halo_pool_bf16": 5, "evfly_tc_conv3x3_halo_pool_rows_bf16": 5, "evfly_tc_conv3x3_halo_out1_bf16": 6}[fn]
                 N, Hp, Wp, vh, vw, Cin, Cout = a[off:off + 7]      # (N, Hp, Wp, vh, vw, Cin, Cout) follow the pointers
                 halo_shapes[(fn.replace("evfly_tc_conv3x3_", ""), N, vh, vw, Cin, Cout)].append((e0, e1))
             return rc

@@ -270,9 +270,10 @@ def test_halo_conv_fused_maxpool_is_bit_identical_to_separate_pool(cuda_lib, N, 
     check_bf16(tc.grid_to_nchw(pooled.data, pooled.vh, pooled.vw), ref, "fused pool")
 
 
-@pytest.mark.parametrize("N,H,W,Cin,Cout", [(3, 12, 17, 256, 512), (2, 29, 39, 256, 256), (1, 16, 26, 512, 256), (5, 5, 7, 256, 256)])
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(3, 12, 17, 256, 512), (2, 29, 39, 256, 256), (1, 16, 26, 512, 256), (5, 5, 7, 256, 256),
+                                            (2, 40, 51, 64, 64), (1, 33, 20, 32, 64), (2, 29, 39, 128, 256), (1, 24, 44, 128, 128), (2, 19, 27, 64, 32)])
 def test_generic_conv_compact_output(cuda_lib, N, H, W, Cin, Cout):
-    """EVFLY_TC_COMPACT: the wide layers write their result on a grid whose pitch is the valid extent; the valid pixels are those of
+    """EVFLY_TC_COMPACT / evfly_tc_conv3x3_halo_compact_bf16: the convs write their result on a grid whose pitch is the valid extent; the valid pixels are those of
     the pitch-preserving call bit for bit, and a second conv on the compact grid equals the second conv on the pitch grid."""
     x = bf(rnd(N, Cin, H, W, seed=1))
     w = bf(rnd(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5))
